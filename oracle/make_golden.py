@@ -1,0 +1,174 @@
+"""Generates tests/golden/*.pt FROM THE UNMODIFIED REFERENCE (imported under oracle/shims; see
+oracle/ref_import.py).  Run in the build container only:  python -m oracle.make_golden [--full]
+
+Every tensor stored under a key starting with "ref_" was produced by /root/reference code
+(models/diffcsp/{cspnet,diffusion,scheduler,utils}.py); the oracle restatement and the CUDA path are
+both tested against them.  Noise is drawn from CPU torch.Generator tapes in the reference's own
+draw order by temporarily replacing torch.rand / randn / randn_like.
+Weights: oracle.diffcsp_oracle.init_params(hp, seed) (default nn.Linear init, heads x0.05); small
+nets are stored, the full-size net is regenerated from its seed and pinned by per-tensor checksums.
+"""
+import argparse
+import contextlib
+import os
+import sys
+import time
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import diffcsp_oracle as O  # noqa: E402
+from oracle import ref_import as R  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+@contextlib.contextmanager
+def noise_tape(seed):
+    gen = torch.Generator().manual_seed(seed)
+    orig = (torch.rand, torch.randn, torch.randn_like)
+    torch.rand = lambda s, **k: orig[0](tuple(s), generator=gen)
+    torch.randn = lambda s, **k: orig[1](tuple(s), generator=gen)
+    torch.randn_like = lambda x: orig[1](tuple(x.shape), generator=gen, dtype=x.dtype)
+    try:
+        yield gen
+    finally:
+        torch.rand, torch.randn, torch.randn_like = orig
+
+
+def checksums(sd):
+    return {k: float(v.double().abs().sum()) for k, v in sd.items()}
+
+
+def synth_crystals(num_atoms, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, N = len(num_atoms), int(sum(num_atoms))
+    return dict(lengths=3 + 5 * torch.rand(B, 3, generator=g), angles=70 + 40 * torch.rand(B, 3, generator=g),
+                frac_coords=torch.rand(N, 3, generator=g), atom_types=torch.randint(1, 101, (N,), generator=g),
+                reward=torch.rand(B, generator=g))
+
+
+def forward_case(hp, sd, ref, num_atoms, seed, t_int):
+    na = torch.tensor(num_atoms)
+    B, N = len(num_atoms), int(na.sum())
+    n2g = torch.repeat_interleave(torch.arange(B), na)
+    g = torch.Generator().manual_seed(seed)
+    t = O.time_embedding(torch.full((B,), t_int), hp["time_dim"])
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g)
+    if hp["edge_style"] == "knn":
+        l = torch.eye(3)[None] * 5 + 0.5 * l
+    with torch.no_grad():
+        pl, px, pt = ref.decoder(t, a, x, l, na, n2g)
+        e, fd = ref.decoder.gen_edges(na, x, l, n2g)
+    return dict(num_atoms=na, t_int=t_int, temb=t, a=a, x=x, l=l, ref_pred_l=pl, ref_pred_x=px, ref_pred_t=pt,
+                ref_edges=e.to(torch.int32), ref_frac_diff=fd)
+
+
+def build(hp, seed_agent=0, seed_prior=1, sigmas_norm=None):
+    torch.manual_seed(1234)   # SigmaScheduler's Monte-Carlo sigma_norm draw (scheduler.py:46-51)
+    ref = R.build_reference_module(hp, sigmas_norm)
+    prior = R.build_reference_module(hp, ref.sigma_scheduler.sigmas_norm)
+    sd, sdp = O.init_params(hp, seed_agent), O.init_params(hp, seed_prior)
+    ref.decoder.load_state_dict(sd)
+    prior.decoder.load_state_dict(sdp)
+    return ref, prior, sd, sdp
+
+
+def ft_case(hp, ref, prior, num_atoms, t_idx, sigma=0.025, accum=50, data_seed=3, noise_seed=11):
+    cr = synth_crystals(num_atoms, data_seed)
+    batch = R.make_batch(num_atoms, **cr)
+    ref.zero_grad()
+    with noise_tape(noise_seed):
+        noised = ref.add_noise(batch, t_idx)
+        sl, ap = ref.calc_sample_loss(noised)
+        with torch.no_grad():
+            _, pp = prior.calc_sample_loss(noised)
+        kl = ref.calc_kl_reg(ap, pp, batch)
+        loss = (batch.reward * sl + kl * (1.1 - batch.reward) * sigma).mean() / accum
+        loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in ref.decoder.named_parameters()}
+    (temb, a_t, x_t, l_t, _, _), (rand_l, tar_x, rand_t), _ = noised
+    return dict(crystals=cr, num_atoms=torch.tensor(num_atoms), t_idx=t_idx, sigma=sigma, accum=accum,
+                noise_seed=noise_seed, ref_temb=temb, ref_a_t=a_t.detach(), ref_x_t=x_t.detach(), ref_l_t=l_t.detach(),
+                ref_rand_l=rand_l, ref_tar_x=tar_x, ref_rand_t=rand_t, ref_sample_loss=sl.detach(),
+                ref_kl=kl.detach(), ref_loss=loss.detach(), ref_agent_pred=[p.detach() for p in ap],
+                ref_prior_pred=[p.detach() for p in pp]), grads
+
+
+def sample_case(hp, ref, num_atoms, seed, step_lr=5e-6):
+    batch = R.make_batch(num_atoms)
+    t0 = time.time()
+    with noise_tape(seed):
+        out, traj = ref.sample(batch, step_lr=step_lr)
+    T = hp["timesteps"]
+    keep = sorted(set([T - 1, T - 2, T // 2, 1, 0]))
+    return dict(num_atoms=torch.tensor(num_atoms), seed=seed, step_lr=step_lr, seconds=time.time() - t0,
+                ref_frac_coords=out["frac_coords"], ref_lattices=out["lattices"], ref_atom_types=out["atom_types"],
+                ref_traj={t: {k: traj[t][k] for k in ("frac_coords", "lattices")} for t in keep if t in traj})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also the full-size net incl. a 1000-step sample (minutes)")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+
+    # --- Monte-Carlo sigmas_norm buffer for T=1000 (copied, never recomputed: SURVEY.md §7 hard parts)
+    hp_full = O.default_hparams()
+    torch.manual_seed(1234)
+    _, _, S, U = R.import_reference()
+    sn1000 = S.SigmaScheduler(1000, hp_full["sigma_begin"], hp_full["sigma_end"]).sigmas_norm.clone()
+    torch.save(dict(sigmas_norm=sn1000, sigma_begin=hp_full["sigma_begin"], sigma_end=hp_full["sigma_end"]),
+               os.path.join(GOLD, "sigmas_norm_T1000.pt"))
+
+    # --- small net, fc + knn: forward, ft timestep with all grads, T=40 sample
+    hp = O.default_hparams(hidden_dim=128, num_layers=2, num_freqs=16, timesteps=40)
+    ref, prior, sd, sdp = build(hp)
+    num_atoms = [3, 1, 7, 20, 5, 12]
+    gold = dict(hp=hp, sd=sd, sd_prior=sdp, sigmas_norm=ref.sigma_scheduler.sigmas_norm.clone(),
+                beta=dict(ref.beta_scheduler.named_buffers()), sigma_sigmas=ref.sigma_scheduler.sigmas.clone())
+    gold["forward_fc"] = forward_case(hp, sd, ref, num_atoms, 1, 17)
+    hp_knn = dict(hp, edge_style="knn", max_neighbors=6)
+    ref.decoder.edge_style, ref.decoder.max_neighbors = "knn", 6
+    gold["hp_knn"] = hp_knn
+    gold["forward_knn"] = forward_case(hp_knn, sd, ref, num_atoms, 2, 9)
+    ref.decoder.edge_style, ref.decoder.max_neighbors = "fc", hp["max_neighbors"]
+    gold["ft"], gold["ft_grads"] = ft_case(hp, ref, prior, num_atoms, 4)
+    gold["sample"] = sample_case(hp, ref, num_atoms, 7)
+    torch.save(gold, os.path.join(GOLD, "small_net.pt"))
+    print("small_net.pt written")
+
+    # --- radius_graph_pbc known answers (reference utils.py:335-601), K = 4 and 20
+    g = torch.Generator().manual_seed(21)
+    na = torch.tensor([2, 9, 20, 1, 14])
+    cr = synth_crystals(na.tolist(), 22)
+    lat = U.lattice_params_to_matrix_torch(cr["lengths"], cr["angles"])
+    cart = torch.einsum('bi,bij->bj', cr["frac_coords"], lat[torch.repeat_interleave(torch.arange(5), na)])
+    rg = dict(num_atoms=na, lattices=lat, frac_coords=cr["frac_coords"], cart=cart)
+    for K in (4, 20):
+        ei, uc, nb = U.radius_graph_pbc(cart, None, None, na, 7.0, K, device="cpu", lattices=lat)
+        rg["ref_K%d" % K] = dict(edge_index=ei.to(torch.int32), cell=uc.to(torch.int8), per_image=nb)
+    torch.save(rg, os.path.join(GOLD, "radius_graph.pt"))
+    print("radius_graph.pt written")
+
+    if args.full:
+        hp = hp_full
+        ref, prior, sd, sdp = build(hp, sigmas_norm=sn1000)
+        num_atoms = [4, 11, 20, 8]
+        gold = dict(hp=hp, seeds=(0, 1), checksums=checksums(sd), checksums_prior=checksums(sdp))
+        gold["forward_fc"] = forward_case(hp, sd, ref, num_atoms, 1, 500)
+        ft, grads = ft_case(hp, ref, prior, num_atoms, 300)
+        gold["ft"] = ft
+        gold["ft_grad_checks"] = {k: dict(abs_sum=float(v.double().abs().sum()), head=v.reshape(-1)[:64].clone())
+                                  for k, v in grads.items()}
+        gold["sample_T1000"] = sample_case(hp, ref, num_atoms, 7)
+        print("1000-step reference sample took %.1f s" % gold["sample_T1000"]["seconds"])
+        torch.save(gold, os.path.join(GOLD, "full_net.pt"))
+        print("full_net.pt written")
+
+
+if __name__ == "__main__":
+    main()
