@@ -1,0 +1,219 @@
+/* libmatinvent_b200 — C ABI of the B200-native DiffCSP/MatInvent hot path.
+ *
+ * The reference (schwallergroup/matinvent) is pure Python and has NO FFI of its own: its boundary is
+ * the duck-typed plugin API of models/suite/base.py:30-59 and pipeline/base.py:26-142.  This header is
+ * the operator ABI that our host-side mirror of that plugin API (matinvent_b200/models, /pipeline,
+ * /memory) binds through ctypes; every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is DEVICE memory owned by the caller (torch tensors' data_ptr()); the library
+ *    never allocates user-visible memory and keeps no global state besides the last-error string;
+ *  - fp32 row-major, int32 indices; `ld*` = leading dimension (elements between consecutive rows);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), graph-capturable;
+ *  - return value: 0 = OK, <0 = error, message via mi_last_error().
+ */
+#ifndef MATINVENT_B200_H
+#define MATINVENT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MI_OK 0
+#define MI_ERR_ARG (-1)
+#define MI_ERR_CUDA (-2)
+#define MI_ERR_UNSUPPORTED (-3)
+
+typedef void* mi_stream_t;
+
+const char* mi_last_error(void);
+int mi_version(void);
+/* fills sm_count / compute capability of the current device */
+int mi_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------- dense blocks (nn.Linear, ATen addmm)
+ * C[M,N] = epilogue(alpha * op(A)[M,K] * op(B)[K,N]).
+ *   transA = 0: A stored [M,K] (lda >= K);  transA = 1: A stored [K,M] (lda >= M)
+ *   transB = 0: B stored [K,N] (ldb >= N);  transB = 1: B stored [N,K] (ldb >= K)  (nn.Linear weight)
+ * Epilogue, per element (m,n), in this order:
+ *   v = alpha*acc (+ bias[n]) (+ g1[idx1[m]][n]) (+ g2[idx2[m]][n]) (+ g3[idx3[m]][n]) (+ beta*C_old)
+ *   if z_out: z_out[m][n] = v
+ *   act == MI_ACT_SILU : v = silu(v);   act == MI_ACT_DSILU : v = v * silu'(z_in[m][n])
+ *   if resid: v += resid[m][n];   C[m][n] = v
+ * splitk > 1 partitions K over gridDim.z and accumulates with atomics; it requires a plain epilogue
+ * (only alpha, and beta == 1 semantics: C += result).
+ * Replaces: nn.Linear / torch.cat / gather / SiLU chains of models/diffcsp/cspnet.py:45-54,59-82,264-294
+ * and their autograd backward. */
+#define MI_ACT_NONE 0
+#define MI_ACT_SILU 1
+#define MI_ACT_DSILU 2
+
+typedef struct {
+    const float* bias;
+    const float* g1; const int* g1_idx; int g1_ld;
+    const float* g2; const int* g2_idx; int g2_ld;
+    const float* g3; const int* g3_idx; int g3_ld;
+    float* z_out; int z_ld;
+    const float* z_in; int zin_ld;
+    const float* resid; int resid_ld;
+    int act;
+    float alpha;
+    float beta;
+    int splitk;
+} mi_epilogue_t;
+
+int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+             int ldb, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- graph construction
+ * Fully-connected intra-crystal edges, row-major by (i, j) incl. i == j
+ * (models/diffcsp/cspnet.py:238-242: block_diag + dense_to_sparse restated arithmetically).
+ *   node_off [B+1], edge_off [B+1] (prefix sums of n_b and n_b^2)
+ * out: edge_src, edge_dst, edge_graph [E]; seg_ptr [N+1] (CSR over edge_src: edges of node i are
+ *      seg_ptr[i]..seg_ptr[i+1]); dst_ptr [N+1] + dst_perm [E] (CSR over edge_dst: edge ids whose
+ *      dst is node j); node_graph [N]. */
+int mi_fc_edges(const int* node_off, const int* edge_off, int B, int N, int E, int* edge_src,
+                int* edge_dst, int* edge_graph, int* seg_ptr, int* dst_ptr, int* dst_perm,
+                int* node_graph, mi_stream_t stream);
+
+/* frac_diff[e] = (x[dst] - x[src]) mod 1 (cspnet.py:242) when cell_off == NULL, else
+ * -( -(x[dst] - x[src] + cell_off[e]) ) restated as x[dst]-x[src]+cell_off (knn, cspnet.py:252-257),
+ * followed by the Fourier basis Phi[e] = [sin(d_c * 2 pi k)]_{c<3,k<F} || [cos(...)] (cspnet.py:12-24),
+ * evaluated with the reference's fp32 arithmetic (arg = d * float(2 pi k)).
+ * frac_diff (nullable) [E,3]; phi [E, 6F] with leading dimension ld_phi. */
+int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, const float* cell_off,
+                    int E, int F, float* frac_diff, float* phi, int ld_phi, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- segment reductions
+ * out[s][:] = scale_s * sum_{k in [ptr[s], ptr[s+1])} X[perm ? perm[k] : k][:]
+ *   mean != 0: scale_s = 1 / max(count, 1) (torch_scatter.scatter(reduce='mean'), cspnet.py:79,281)
+ *   mean == 0: plain sum.  accumulate != 0: out += result.
+ * H must be a multiple of 4 and rows 16-byte aligned.  This is the edge-scatter roofline kernel. */
+int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
+                      int S, int H, int mean, int accumulate, mi_stream_t stream);
+
+/* dX[e][:] = dOut[idx[e]][:] * (inv_count ? 1/max(cnt(idx[e]),1) : 1) * (z ? silu'(z[e][:]) : 1)
+ * (backward of segment mean + SiLU).  idx nullable -> identity; ptr = CSR used for counts (nullable ->
+ * no scaling). */
+int mi_gather_rows_dsilu(const float* dOut, int ldd, const int* idx, const int* ptr, const float* z,
+                         int ldz, float* dX, int ldx, int E, int H, mi_stream_t stream);
+
+/* out[n] (+)= sum_m X[m][n]  (bias gradients) */
+int mi_colsum(const float* X, int ldx, int M, int N, float* out, int accumulate, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- LayerNorm (cspnet.py:57,86-88,142,277)
+ */
+int mi_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                     float* mean, float* rstd, int rows, int H, float eps, mi_stream_t stream);
+/* dx (+)= LN backward; dgamma/dbeta += (atomics) */
+int mi_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma,
+                     const float* mean, const float* rstd, float* dx, int lddx, int accumulate_dx,
+                     float* dgamma, float* dbeta, int rows, int H, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- small per-crystal pieces
+ * ips[b] = vec(L_b L_b^T)  (cspnet.py:67-72) */
+int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stream);
+/* out[b] = A[b] (3x3) @ L[b] (3x3)   (cspnet.py:288-289); transL != 0 -> A[b] @ L[b]^T (its backward) */
+int mi_bmm3(const float* A, const float* L, float* out, int B, int transL, mi_stream_t stream);
+/* SinusoidalTimeEmbeddings (diffusion.py:53-66): out[b] = [sin(t_b f_k) || cos(t_b f_k)], dim even;
+ * freq [dim/2] = exp(-k ln(1e4)/(dim/2-1)) is a host-built table (bit-identical to the reference's). */
+int mi_time_embed(const int* t, const float* freq, int B, int dim, float* out, mi_stream_t stream);
+/* lattice_params_to_matrix_torch (utils.py:68-96); lengths/angles [B,3] (degrees) -> L [B,3,3] */
+int mi_lattice_params_to_matrix(const float* lengths, const float* angles, float* L, int B,
+                                mi_stream_t stream);
+/* lattices_to_params_shape (sample.py:103-114) + argmax(atom_types)+1 (sample.py:182) */
+int mi_lattice_matrix_to_params(const float* L, float* lengths, float* angles, int B,
+                                mi_stream_t stream);
+int mi_argmax_rows(const float* a, int lda, int rows, int cols, int add, int* out, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- reverse diffusion updates
+ * Scalars of step t (diffusion.py:300-307,324-325,341-343) come from a device table built once on the
+ * host in fp32: coef[t] = {sqrt(sigma_norm_t), step_c, std_c, step_p, std_p, c0, c1, sigma^beta_t}.
+ * The row is selected by *t_dev when t_dev != NULL (so ONE captured CUDA graph serves every step),
+ * else by t_host.  Noise pointers may be NULL (treated as zeros: t == 1).
+ * corrector (diffusion.py:327-330): x_half = x - step_c * (pred_x * sqrt_sn) + std_c * z_x */
+int mi_reverse_corrector(const float* x, const float* pred_x, const float* z_x, float* x_half, int N,
+                         const float* coef, const int* t_dev, int t_host, mi_stream_t stream);
+/* predictor (diffusion.py:345-351,386): x = ((x_half - step_p*pred_x*sqrt_sn + std_p*z_x) % 1) % 1;
+ * l = c0*(l - c1*pred_l) + sig*z_l ; a = c0*(a - c1*pred_a) + sig*z_a  (in place on l, a) */
+int mi_reverse_predictor(const float* x_half, const float* pred_x, const float* z_x, float* x, int N,
+                         float* l, const float* pred_l, const float* z_l, int B, float* a,
+                         const float* pred_a, const float* z_a, int A, const float* coef,
+                         const int* t_dev, int t_host, mi_stream_t stream);
+/* temb[b][:] = ttab[*t_dev][:] for every crystal (diffusion.py:297-298); *t_dev -= 1 */
+int mi_sampler_step_begin(const int* t_dev, const float* ttab, float* temb, int B, int T,
+                          mi_stream_t stream);
+int mi_sampler_step_end(int* t_dev, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- forward noising + losses
+ * add_noise (diffusion.py:81-119) for one integer time shared by the batch:
+ *   l_t = c0*L0 + c1*z_l ; x_t = (x0 + sigma*z_x) % 1 ; a_t = c0*onehot(Z-1) + c1*z_a ;
+ *   tar_x = d_log_p_wrapped_normal(sigma*z_x, sigma) / sqrt(sigma_norm)  (scheduler.py:39-43) */
+int mi_add_noise(const float* L0, const float* x0, const int* Z, const float* z_l, const float* z_x,
+                 const float* z_a, int B, int N, int A, float c0, float c1, float sigma,
+                 float sigma_norm, float* l_t, float* x_t, float* a_t, float* tar_x,
+                 mi_stream_t stream);
+
+/* Per-crystal denoising loss (diffusion.py:121-138), KL proxy (diffusion.py:140-149) and the
+ * reward-weighted objective of MatInvent.ft_step (pipeline/mat_invent.py:152-163), with the
+ * gradient of   J = scale * sum_b [ w_loss[b]*loss_b + w_kl[b]*kl_b ]   w.r.t. the agent's
+ * predictions.  prior_* may be NULL (kl = 0).  d_* may be NULL (forward only).
+ * Host passes w_loss = reward, w_kl = sigma*(1.1-reward), scale = 1/(B_global*accum_steps), or the
+ * upstream autograd gradient in the plugin path. */
+int mi_rl_loss(const float* pred_l, const float* pred_x, const float* pred_a, const float* tgt_l,
+               const float* tgt_x, const float* tgt_a, const float* prior_l, const float* prior_x,
+               const float* prior_a, const int* node_off, int B, int A, float cost_l, float cost_x,
+               float cost_a, const float* w_loss, const float* w_kl, float scale, float* loss,
+               float* kl, float* d_l, float* d_x, float* d_a, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * torch.optim.Adam defaults (pipeline/mat_invent.py:136,166): flat fp32 buffers,
+ *   m = m + (g-m)*(1-b1) ; v = b2*v + (1-b2)*g*g ;
+ *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps);  g is multiplied by grad_scale first and
+ * zeroed afterwards when zero_grad != 0. */
+int mi_adam_step(float* p, float* g, float* m, float* v, long long n, double lr, double b1, double b2,
+                 double eps, int step, float grad_scale, int zero_grad, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- RNG
+ * Philox4x32-10 + Box-Muller standard normals / uniforms in [0,1): element i of the call uses counter
+ * (offset + i/4), key = seed.  For CUDA-graph replay, `offset_dev` (nullable) is a device u64 added to
+ * `offset` and, when advance != 0, incremented by ceil(n/4) by the kernel afterwards. */
+int mi_philox_normal(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                     unsigned long long* offset_dev, int advance, mi_stream_t stream);
+int mi_philox_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                      unsigned long long* offset_dev, int advance, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- periodic neighbour list
+ * radius_graph_pbc + get_max_neighbors_mask (models/diffcsp/utils.py:335-514, 517-601) followed by
+ * reorder_symmetric_edges (cspnet.py:159-234) and the sign flip of gen_edges (cspnet.py:252-257),
+ * emitted sorted by source node (the network is invariant to edge order).
+ * One CTA per crystal (n_b <= max_n <= 128).  Capacity: each node holds at most `cap` edges; the true
+ * count is written to deg[N] (and to overflow[0] != 0 if any node exceeded cap).
+ * out: edge_dst [N*cap], cell_off [N*cap,3] (as float), deg [N]; compact with mi_compact_edges. */
+int mi_radius_graph_pbc(const float* x, const float* L, const int* node_off, int B, int N, int max_n,
+                        int max_neighbors, int cap, int* edge_dst, float* cell_off, int* deg,
+                        int* overflow, mi_stream_t stream);
+/* seg_ptr = exclusive scan of deg (single CTA), then gather padded rows into CSR arrays */
+int mi_compact_edges(const int* deg, int N, int cap, const int* edge_dst_pad, const float* cell_pad,
+                     const int* node_graph, int* seg_ptr, int* edge_src, int* edge_dst,
+                     int* edge_graph, float* cell_off, int E_cap, mi_stream_t stream);
+/* CSR over destinations from (edge_dst) : dst_ptr [N+1], dst_perm [E] (E read from seg_ptr[N]) */
+int mi_build_dst_csr(const int* seg_ptr, const int* edge_dst, int N, int E_cap, int* dst_ptr,
+                     int* dst_perm, int* work, mi_stream_t stream);
+
+/* ---------------------------------------------------------------- device replay buffer
+ * memory/replay_buffer.py:32-73 on padded SoA rows: given keys (64-bit reduced-composition hash) and
+ * rewards of `n` candidate rows (old rows first), compute the kept row order:
+ * sort by reward desc (stable), drop later duplicates of a key, keep the first `buffer_size`, keep
+ * reward > cutoff.  out_idx [n] (first *out_count entries valid). Single CTA (n <= 16384). */
+int mi_replay_select(const unsigned long long* keys, const float* rewards, int n, int buffer_size,
+                     float cutoff, int* out_idx, int* out_count, mi_stream_t stream);
+/* key[b] = hash of the gcd-reduced element-count vector of crystal b (Z in 1..100)
+ * (pymatgen reduced_formula equivalence class, memory/replay_buffer.py:38) */
+int mi_composition_key(const int* Z, const int* node_off, int B, unsigned long long* keys,
+                       mi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,474 @@
+"""CSPNet score network on libmatinvent_b200 (forward AND hand-written backward).
+
+Host-side mirror of the reference's `CSPNet` (models/diffcsp/cspnet.py:93-294): same constructor
+arguments, same `forward(t, atom_types, frac_coords, lattices, num_atoms, node2graph)` returning
+`(lattice_out [B,3,3], coord_out [N,3], type_out [N,100])`, same `state_dict` names, so it drops in
+under DiffCSPModule / models/suite.  Everything arithmetic runs in the CUDA library:
+
+  * weights live in ONE flat fp32 buffer (flat Adam + a single gradient all-reduce); the first edge
+    linear (cspnet.py:45, in = [h_i | h_j | vec(L L^T) | Phi]) is stored SPLIT as W_pq = [W_hi; W_hj],
+    W_L, W_F so that  W1 . [h_i|h_j|ips|Phi] = P_i + Q_j + C_b + Phi_ij W_F^T  — the h_i / h_j parts
+    become per-NODE GEMMs (n instead of n^2 rows) and the `[E,1801]` concat is never formed;
+  * the Fourier basis (cspnet.py:12-24) is evaluated once per forward, not once per layer (:65-66);
+  * edges are static per batch (graph.py) instead of block_diag + nonzero per forward (:238-242).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...ops import ACT_DSILU, ACT_NONE, ACT_SILU
+from .graph import CrystalGraph
+
+MAX_ATOMIC_NUM = 100
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class _Workspace:
+    """Preallocated activations for one (graph size, mode); addresses are stable (CUDA-graph safe)."""
+
+    def __init__(self, net, g, train):
+        dev, f32 = g.device, torch.float32
+        H, A, F6, L = net.hidden_dim, net.max_atoms, 6 * net.num_freqs, net.num_layers
+        N, E, B = g.N, g.E, g.B
+        nl = L if train else 1
+
+        def buf(*shape):
+            return torch.empty(*shape, device=dev, dtype=f32)
+
+        self.train = train
+        self.phi = buf(E, F6)
+        self.ips = buf(B, 9)
+        self.tb = buf(B, H)
+        self.cb = buf(B, H)
+        self.h0 = buf(N, H)
+        self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] * (L + 1)
+        self.cat = [buf(N, 2 * H) for _ in range(nl)]
+        self.pq = buf(N, 2 * H)
+        self.a1 = [buf(E, H) for _ in range(nl)]
+        self.a2 = buf(E, H)
+        self.an1 = [buf(N, H) for _ in range(nl)]
+        self.hf = buf(N, H)
+        self.gmean = buf(B, H)
+        self.lat9 = buf(B, 9)
+        self.pred_l = buf(B, 3, 3)
+        self.pred_x = buf(N, 3)
+        self.pred_a = buf(N, A)
+        if train:
+            self.z1 = [buf(E, H) for _ in range(L)]
+            self.z2 = [buf(E, H) for _ in range(L)]
+            self.zn1 = [buf(N, H) for _ in range(L)]
+            self.zn2 = [buf(N, H) for _ in range(L)]
+            self.ln_mean = [buf(N) for _ in range(L + 1)]
+            self.ln_rstd = [buf(N) for _ in range(L + 1)]
+            # backward scratch
+            self.dh = buf(N, H)
+            self.dhf = buf(N, H)
+            self.dcat = buf(N, 2 * H)
+            self.dpq = buf(N, 2 * H)
+            self.dzn = buf(N, H)
+            self.dzn1 = buf(N, H)
+            self.dz2 = buf(E, H)
+            self.dz1 = buf(E, H)
+            self.dcb = buf(B, H)
+            self.dg = buf(B, H)
+            self.dgn = buf(N, H)
+            self.dlat9 = buf(B, 9)
+            self.dtb = buf(B, H)
+
+
+class CSPNet(nn.Module):
+    def __init__(self, hidden_dim=128, latent_dim=256, num_layers=4, max_atoms=100, act_fn="silu",
+                 dis_emb="sin", num_freqs=10, edge_style="fc", cutoff=6.0, max_neighbors=20, ln=False,
+                 ip=True, smooth=False, pred_type=False, pred_scalar=False, device=None):
+        super().__init__()
+        if act_fn != "silu" or dis_emb != "sin":
+            raise NotImplementedError("matinvent_b200 CSPNet implements act_fn='silu', dis_emb='sin' (the MatInvent config)")
+        if not (smooth and pred_type) or pred_scalar:
+            raise NotImplementedError("matinvent_b200 CSPNet implements the smooth=True, pred_type=True generation head "
+                                      "(models/diffcsp/diffusion.py:73)")
+        if hidden_dim % 4 or latent_dim % 4 or max_atoms % 4:
+            raise ValueError("hidden_dim, latent_dim and max_atoms must be multiples of 4")
+        self.hidden_dim, self.latent_dim, self.num_layers = hidden_dim, latent_dim, num_layers
+        self.max_atoms, self.num_freqs = max_atoms, num_freqs
+        self.edge_style, self.cutoff, self.max_neighbors = edge_style, cutoff, max_neighbors
+        self.ln, self.ip = ln, ip
+        dev = torch.device(device if device is not None else "cuda")
+        H, A, T, F6 = hidden_dim, max_atoms, latent_dim, 6 * num_freqs
+        spec = [("emb_w", (H, A)), ("emb_b", (H,)), ("lat_w_h", (H, H)), ("lat_w_t", (H, T)), ("lat_b", (H,))]
+        for i in range(num_layers):
+            p = "l%d." % i
+            spec += [(p + "ln_g", (H,)), (p + "ln_b", (H,)), (p + "w_pq", (2 * H, H)), (p + "w_l", (H, 9)),
+                     (p + "w_f", (H, F6)), (p + "b1", (H,)), (p + "w2", (H, H)), (p + "b2", (H,)),
+                     (p + "wn1", (H, 2 * H)), (p + "bn1", (H,)), (p + "wn2", (H, H)), (p + "bn2", (H,))]
+        spec += [("fin_g", (H,)), ("fin_b", (H,)), ("coord_w", (3, H)), ("lattice_w", (9, H)),
+                 ("type_w", (MAX_ATOMIC_NUM, H)), ("type_b", (MAX_ATOMIC_NUM,))]
+        self._spec = spec
+        off, self._slices = 0, OrderedDict()
+        for name, shape in spec:
+            n = math.prod(shape)
+            self._slices[name] = (off, n, shape)
+            off += _pad4(n)
+        self.flat = nn.Parameter(torch.zeros(off, device=dev, dtype=torch.float32))
+        self._views, self._gviews = {}, {}
+        self._flat_grad = None
+        self._ws = {}
+        self._graphs = {}
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ parameters
+    def _rebuild_views(self):
+        d = self.flat.data
+        self._views = {k: d[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
+        if self._flat_grad is not None:
+            g = self._flat_grad
+            self._gviews = {k: g[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._flat_grad = None
+        self._gviews = {}
+        self._rebuild_views()
+        self._ws, self._graphs = {}, {}
+        return r
+
+    @property
+    def device(self):
+        return self.flat.device
+
+    def w(self, name):
+        return self._views[name]
+
+    def flat_grad(self):
+        """Flat fp32 gradient buffer, aliased by `self.flat.grad` (so torch.optim / autograd see it)."""
+        if self._flat_grad is None:
+            self._flat_grad = torch.zeros_like(self.flat.data)
+            self._rebuild_views()
+        cur = self.flat.grad
+        if cur is None:                       # never attached, or dropped by zero_grad(set_to_none=True)
+            self._flat_grad.zero_()
+            self.flat.grad = self._flat_grad
+        elif cur.data_ptr() != self._flat_grad.data_ptr():
+            self._flat_grad.copy_(cur)
+            self.flat.grad = self._flat_grad
+        return self._flat_grad
+
+    def reset_parameters(self, seed=None):
+        """nn.Linear / nn.LayerNorm default init of the reference's modules (uniform +-1/sqrt(fan_in))."""
+        gen = None
+        if seed is not None:
+            gen = torch.Generator().manual_seed(seed)
+        sd = OrderedDict()
+        H, A, T, F6 = self.hidden_dim, self.max_atoms, self.latent_dim, 6 * self.num_freqs
+
+        def lin(name, out_f, in_f, bias=True):
+            k = 1.0 / math.sqrt(in_f)
+            sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * k
+            if bias:
+                sd[name + ".bias"] = (torch.rand(out_f, generator=gen) * 2 - 1) * k
+
+        lin("node_embedding", H, A)
+        lin("atom_latent_emb", H, H + T)
+        for i in range(self.num_layers):
+            p = "csp_layer_%d." % i
+            lin(p + "edge_mlp.0", H, 2 * H + 9 + F6)
+            lin(p + "edge_mlp.2", H, H)
+            lin(p + "node_mlp.0", H, 2 * H)
+            lin(p + "node_mlp.2", H, H)
+            if self.ln:
+                sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"] = torch.ones(H), torch.zeros(H)
+        lin("coord_out", 3, H, bias=False)
+        lin("lattice_out", 9, H, bias=False)
+        if self.ln:
+            sd["final_layer_norm.weight"], sd["final_layer_norm.bias"] = torch.ones(H), torch.zeros(H)
+        lin("type_out", MAX_ATOMIC_NUM, H)
+        self._load_reference_state(sd)
+
+    def _load_reference_state(self, sd, prefix=""):
+        """Scatter reference-named tensors (cspnet.py:118-146 module names) into the flat buffer."""
+        H = self.hidden_dim
+        self._rebuild_views()
+        v = self._views
+
+        def put(dst, src):
+            if tuple(src.shape) != tuple(dst.shape):
+                raise ValueError("shape mismatch %s vs %s" % (tuple(src.shape), tuple(dst.shape)))
+            dst.copy_(src.to(dst.device, torch.float32))
+
+        g = lambda k: sd[prefix + k]
+        put(v["emb_w"], g("node_embedding.weight")), put(v["emb_b"], g("node_embedding.bias"))
+        wl = g("atom_latent_emb.weight")
+        put(v["lat_w_h"], wl[:, :H]), put(v["lat_w_t"], wl[:, H:]), put(v["lat_b"], g("atom_latent_emb.bias"))
+        for i in range(self.num_layers):
+            p, q = "csp_layer_%d." % i, "l%d." % i
+            w1 = g(p + "edge_mlp.0.weight")
+            put(v[q + "w_pq"][:H], w1[:, :H]), put(v[q + "w_pq"][H:], w1[:, H:2 * H])
+            put(v[q + "w_l"], w1[:, 2 * H:2 * H + 9]), put(v[q + "w_f"], w1[:, 2 * H + 9:])
+            put(v[q + "b1"], g(p + "edge_mlp.0.bias"))
+            put(v[q + "w2"], g(p + "edge_mlp.2.weight")), put(v[q + "b2"], g(p + "edge_mlp.2.bias"))
+            put(v[q + "wn1"], g(p + "node_mlp.0.weight")), put(v[q + "bn1"], g(p + "node_mlp.0.bias"))
+            put(v[q + "wn2"], g(p + "node_mlp.2.weight")), put(v[q + "bn2"], g(p + "node_mlp.2.bias"))
+            if self.ln:
+                put(v[q + "ln_g"], g(p + "layer_norm.weight")), put(v[q + "ln_b"], g(p + "layer_norm.bias"))
+            else:
+                v[q + "ln_g"].fill_(1.0), v[q + "ln_b"].zero_()
+        put(v["coord_w"], g("coord_out.weight")), put(v["lattice_w"], g("lattice_out.weight"))
+        if self.ln:
+            put(v["fin_g"], g("final_layer_norm.weight")), put(v["fin_b"], g("final_layer_norm.bias"))
+        else:
+            v["fin_g"].fill_(1.0), v["fin_b"].zero_()
+        put(v["type_w"], g("type_out.weight")), put(v["type_b"], g("type_out.bias"))
+
+    def _reference_named(self, views):
+        """Inverse of _load_reference_state: reference-named tensors from native blocks."""
+        H = self.hidden_dim
+        o = OrderedDict()
+        o["node_embedding.weight"], o["node_embedding.bias"] = views["emb_w"].clone(), views["emb_b"].clone()
+        o["atom_latent_emb.weight"] = torch.cat([views["lat_w_h"], views["lat_w_t"]], dim=1)
+        o["atom_latent_emb.bias"] = views["lat_b"].clone()
+        for i in range(self.num_layers):
+            p, q = "csp_layer_%d." % i, "l%d." % i
+            o[p + "edge_mlp.0.weight"] = torch.cat([views[q + "w_pq"][:H], views[q + "w_pq"][H:], views[q + "w_l"],
+                                                    views[q + "w_f"]], dim=1)
+            o[p + "edge_mlp.0.bias"] = views[q + "b1"].clone()
+            o[p + "edge_mlp.2.weight"], o[p + "edge_mlp.2.bias"] = views[q + "w2"].clone(), views[q + "b2"].clone()
+            o[p + "node_mlp.0.weight"], o[p + "node_mlp.0.bias"] = views[q + "wn1"].clone(), views[q + "bn1"].clone()
+            o[p + "node_mlp.2.weight"], o[p + "node_mlp.2.bias"] = views[q + "wn2"].clone(), views[q + "bn2"].clone()
+            if self.ln:
+                o[p + "layer_norm.weight"], o[p + "layer_norm.bias"] = views[q + "ln_g"].clone(), views[q + "ln_b"].clone()
+        o["coord_out.weight"], o["lattice_out.weight"] = views["coord_w"].clone(), views["lattice_w"].clone()
+        if self.ln:
+            o["final_layer_norm.weight"], o["final_layer_norm.bias"] = views["fin_g"].clone(), views["fin_b"].clone()
+        o["type_out.weight"], o["type_out.bias"] = views["type_w"].clone(), views["type_b"].clone()
+        return o
+
+    def state_dict(self, destination=None, prefix="", keep_vars=False):
+        d = destination if destination is not None else OrderedDict()
+        for k, t in self._reference_named(self._views).items():
+            d[prefix + k] = t
+        return d
+
+    def reference_named_grads(self):
+        self.flat_grad()
+        return self._reference_named(self._gviews)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        try:
+            self._load_reference_state(state_dict, prefix)
+        except KeyError as e:
+            missing_keys.append(str(e))
+
+    # ------------------------------------------------------------------ graphs / workspaces
+    def graph_for(self, num_atoms):
+        key = tuple(int(v) for v in torch.as_tensor(num_atoms).reshape(-1).tolist())
+        g = self._graphs.get(key)
+        if g is None:
+            if self.edge_style == "fc":
+                g = CrystalGraph(key, self.device)
+            else:
+                from .knn import KnnGraph
+                g = KnnGraph(key, self.device, self.max_neighbors)
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+                self._ws.clear()
+            self._graphs[key] = g
+        return g
+
+    def workspace(self, g, train):
+        key = (id(g), bool(train))
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = _Workspace(self, g, train)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None):
+        """Score network on a prebuilt graph.  temb [B,T], a [N,A], x [N,3], l [B,3,3] fp32 CUDA.
+        heads = which of (lattice, coord, type) outputs to compute.  Returns views into the workspace."""
+        W, H, F = self._views, self.hidden_dim, self.num_freqs
+        N, E, B, L = g.N, g.E, g.B, self.num_layers
+        ws = ws or self.workspace(g, train)
+        if self.edge_style != "fc":
+            g.rebuild(x, l)
+            E = g.E
+        # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
+        ops.sgemm(a, W["emb_w"], ws.h0, bias=W["emb_b"], M=N)
+        ops.sgemm(temb, W["lat_w_t"], ws.tb, bias=W["lat_b"], M=B)
+        ops.sgemm(ws.h0, W["lat_w_h"], ws.h[0], gathers=[(ws.tb, g.node_graph)], M=N)
+        ops.lattice_ip(l, ws.ips, B)
+        ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi)
+        for i in range(L):
+            q = "l%d." % i
+            k = i if train else 0
+            cat, a1, an1 = ws.cat[k], ws.a1[k], ws.an1[k]
+            h_in, h_out = ws.h[i], ws.h[i + 1]
+            hn = cat[:, :H]
+            if self.ln:
+                ops.layernorm_fwd(h_in, W[q + "ln_g"], W[q + "ln_b"], hn, N, H,
+                                  ws.ln_mean[i] if train else None, ws.ln_rstd[i] if train else None)
+            else:
+                hn.copy_(h_in)
+            # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
+            ops.sgemm(hn, W[q + "w_pq"], ws.pq, M=N)
+            ops.sgemm(ws.ips, W[q + "w_l"], ws.cb, bias=W[q + "b1"], M=B)
+            ops.sgemm(ws.phi, W[q + "w_f"], a1, M=E,
+                      gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
+                      z_out=ws.z1[i] if train else None, act=ACT_SILU)
+            ops.sgemm(a1, W[q + "w2"], ws.a2, M=E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU)
+            # scatter-mean over the source node (cspnet.py:79)
+            ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True)
+            # node model + residual (cspnet.py:77-91)
+            ops.sgemm(cat, W[q + "wn1"], an1, M=N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU)
+            ops.sgemm(an1, W[q + "wn2"], h_out, M=N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
+                      act=ACT_SILU, resid=h_in)
+        hL = ws.h[L]
+        if self.ln:
+            ops.layernorm_fwd(hL, W["fin_g"], W["fin_b"], ws.hf, N, H,
+                              ws.ln_mean[L] if train else None, ws.ln_rstd[L] if train else None)
+            hf = ws.hf
+        else:
+            hf = hL
+        ws.hf_used = hf
+        if heads[1]:
+            ops.sgemm(hf, W["coord_w"], ws.pred_x, M=N)
+        if heads[0]:
+            ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True)
+            if self.ip:
+                ops.sgemm(ws.gmean, W["lattice_w"], ws.lat9, M=B)
+                ops.bmm3(ws.lat9, l, ws.pred_l, B)
+            else:
+                ops.sgemm(ws.gmean, W["lattice_w"], ws.pred_l.view(B, 9), M=B)
+        if heads[2]:
+            ops.sgemm(hf, W["type_w"], ws.pred_a, bias=W["type_b"], M=N)
+        return ws.pred_l, ws.pred_x, ws.pred_a
+
+    # ------------------------------------------------------------------ backward
+    @staticmethod
+    def _splitk(M, N, K):
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        want = max(1, (2 * 148) // tiles)
+        return max(2, min(want, (K + 255) // 256, 64))
+
+    def _wgrad(self, dY, X, gname, M, N, K):
+        """grad[gname] [M,N] += dY[K,M]^T @ X[K,N]   (sum over rows: nodes / edges / crystals)"""
+        ops.sgemm(dY, X, self._gviews[gname], transA=True, transB=False, M=M, N=N, K=K, beta=1.0,
+                  splitk=self._splitk(M, N, K))
+
+    def backward_graph(self, g, temb, a, x, l, d_l, d_x, d_a, ws=None):
+        """Accumulate d(objective)/d(weights) into the flat gradient buffer given the gradients w.r.t. the
+        three outputs of the matching `forward_graph(..., train=True)` call (activations in `ws`)."""
+        self.flat_grad()
+        W, G, H = self._views, self._gviews, self.hidden_dim
+        N, E, B, L, A = g.N, g.E, g.B, self.num_layers, MAX_ATOMIC_NUM
+        F6, T = 6 * self.num_freqs, self.latent_dim
+        ws = ws or self.workspace(g, True)
+        hf = ws.hf if self.ln else ws.h[L]
+        # ---- heads (cspnet.py:276-294)
+        if self.ip:
+            ops.bmm3(d_l, l, ws.dlat9, B, transL=True)
+            dlat9 = ws.dlat9
+        else:
+            dlat9 = d_l.view(B, 9)
+        self._wgrad(dlat9, ws.gmean, "lattice_w", 9, H, B)
+        ops.sgemm(dlat9, W["lattice_w"], ws.dg, transB=False, M=B, N=H, K=9)
+        ops.gather_rows_dsilu(ws.dg, g.node_graph, g.node_off, None, ws.dgn, N, H)
+        self._wgrad(d_x, hf, "coord_w", 3, H, N)
+        self._wgrad(d_a, hf, "type_w", A, H, N)
+        ops.colsum(d_a, N, A, G["type_b"])
+        ops.sgemm(d_a, W["type_w"], ws.dhf, transB=False, M=N, N=H, K=A, gathers=[(ws.dgn, None)])
+        ops.sgemm(d_x, W["coord_w"], ws.dhf, transB=False, M=N, N=H, K=3, beta=1.0)
+        if self.ln:
+            ops.layernorm_bwd(ws.dhf, ws.h[L], W["fin_g"], ws.ln_mean[L], ws.ln_rstd[L], ws.dh, G["fin_g"], G["fin_b"],
+                              N, H)
+            dh = ws.dh
+        else:
+            ws.dh.copy_(ws.dhf)
+            dh = ws.dh
+        # ---- layers, reversed
+        for i in reversed(range(L)):
+            q = "l%d." % i
+            cat, a1, an1 = ws.cat[i], ws.a1[i], ws.an1[i]
+            # h_out = h_in + silu(zn2);  zn2 = an1 wn2^T + bn2;  an1 = silu(zn1);  zn1 = cat wn1^T + bn1
+            ops.gather_rows_dsilu(dh, None, None, ws.zn2[i], ws.dzn, N, H)
+            self._wgrad(ws.dzn, an1, q + "wn2", H, H, N)
+            ops.colsum(ws.dzn, N, H, G[q + "bn2"])
+            ops.sgemm(ws.dzn, W[q + "wn2"], ws.dzn1, transB=False, M=N, N=H, K=H, act=ACT_DSILU, z_in=ws.zn1[i])
+            self._wgrad(ws.dzn1, cat, q + "wn1", H, 2 * H, N)
+            ops.colsum(ws.dzn1, N, H, G[q + "bn1"])
+            ops.sgemm(ws.dzn1, W[q + "wn1"], ws.dcat, transB=False, M=N, N=2 * H, K=H)
+            # agg = mean_j a2 ; a2 = silu(z2) ; z2 = a1 w2^T + b2
+            ops.gather_rows_dsilu(ws.dcat[:, H:], g.edge_src, g.seg_ptr, ws.z2[i], ws.dz2, E, H)
+            self._wgrad(ws.dz2, a1, q + "w2", H, H, E)
+            ops.colsum(ws.dz2, E, H, G[q + "b2"])
+            # a1 = silu(z1) ; z1 = Phi w_f^T + P[src] + Q[dst] + C[graph]
+            ops.sgemm(ws.dz2, W[q + "w2"], ws.dz1, transB=False, M=E, N=H, K=H, act=ACT_DSILU, z_in=ws.z1[i])
+            self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E)
+            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False)
+            ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False)
+            ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False)
+            ops.colsum(ws.dcb, B, H, G[q + "b1"])
+            self._wgrad(ws.dcb, ws.ips, q + "w_l", H, 9, B)
+            self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N)
+            # d hn = dcat[:, :H] + dpq @ w_pq   (written over dcat[:, :H])
+            ops.sgemm(ws.dpq, W[q + "w_pq"], ws.dcat[:, :H], transB=False, M=N, N=H, K=2 * H, beta=1.0)
+            if self.ln:
+                ops.layernorm_bwd(ws.dcat[:, :H], ws.h[i], W[q + "ln_g"], ws.ln_mean[i], ws.ln_rstd[i], dh,
+                                  G[q + "ln_g"], G[q + "ln_b"], N, H, accumulate_dx=True)
+            else:
+                dh.add_(ws.dcat[:, :H])
+        # ---- embedding
+        self._wgrad(dh, ws.h0, "lat_w_h", H, H, N)
+        ops.segment_reduce(dh, g.node_off, ws.dtb, B, H, mean=False)
+        ops.colsum(ws.dtb, B, H, G["lat_b"])
+        self._wgrad(ws.dtb, temb, "lat_w_t", H, T, B)
+        ops.sgemm(dh, W["lat_w_h"], ws.dzn, transB=False, M=N, N=H, K=H)
+        self._wgrad(ws.dzn, a, "emb_w", H, self.max_atoms, N)
+        ops.colsum(ws.dzn, N, H, G["emb_b"])
+
+    # ------------------------------------------------------------------ reference-facing forward
+    def forward(self, t, atom_types, frac_coords, lattices, num_atoms, node2graph):
+        """models/diffcsp/cspnet.py:260-294.  With autograd enabled and trainable weights the call is
+        differentiable w.r.t. the weights (torch.autograd.Function over the hand-written backward)."""
+        g = self.graph_for(num_atoms)
+        temb = t.to(torch.float32).contiguous()
+        a = atom_types.to(torch.float32).contiguous()
+        x = frac_coords.to(torch.float32).contiguous()
+        l = lattices.to(torch.float32).contiguous()
+        if torch.is_grad_enabled() and self.flat.requires_grad:
+            return _CSPNetFunction.apply(self.flat, self, g, temb, a, x, l)
+        pl, px, pa = self.forward_graph(g, temb, a, x, l, train=False)
+        return pl.clone(), px.clone(), pa.clone()
+
+
+class _CSPNetFunction(torch.autograd.Function):
+    """Autograd bridge for the plugin path (pipeline/mat_invent.py:152-164 calls `.backward()`)."""
+
+    @staticmethod
+    def forward(ctx, flat, net, g, temb, a, x, l):
+        pl, px, pa = net.forward_graph(g, temb, a, x, l, train=True)
+        ctx.net, ctx.g = net, g
+        ctx.save_for_backward(temb, a, x, l)
+        return pl.clone(), px.clone(), pa.clone()
+
+    @staticmethod
+    def backward(ctx, d_l, d_x, d_a):
+        net, g = ctx.net, ctx.g
+        temb, a, x, l = ctx.saved_tensors
+        B, N = g.B, g.N
+
+        def z(t, shape):
+            return torch.zeros(shape, device=net.device) if t is None else t.contiguous()
+
+        gbuf = net.flat_grad()
+        before = gbuf.clone()
+        net.backward_graph(g, temb, a, x, l, z(d_l, (B, 3, 3)), z(d_x, (N, 3)), z(d_a, (N, MAX_ATOMIC_NUM)))
+        delta = gbuf - before          # autograd accumulates the returned gradient into flat.grad itself
+        gbuf.copy_(before)
+        return delta, None, None, None, None, None, None

@@ -1,0 +1,255 @@
+"""Tensor-level wrappers over the C ABI (include/matinvent_b200.h).  torch is used for device memory
+and streams only; every arithmetic op below runs in libmatinvent_b200.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check
+
+ACT_NONE, ACT_SILU, ACT_DSILU = 0, 1, 2
+
+
+def lib():
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t, name="tensor"):
+    if t is None:
+        return
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError("%s must be a CUDA float32 tensor (got %s on %s)" % (name, t.dtype, t.device))
+
+
+def _i32(t, name="tensor"):
+    if t is None:
+        return
+    if t.dtype != torch.int32 or not t.is_cuda:
+        raise TypeError("%s must be a CUDA int32 tensor (got %s on %s)" % (name, t.dtype, t.device))
+
+
+def _ld(t):
+    """leading dimension of a 2-D row-major view (last dim contiguous)."""
+    if t.dim() == 1:
+        return t.shape[0]
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise ValueError("last dimension must be contiguous")
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[-1], t.stride(0))
+
+
+def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None, gathers=(), z_out=None,
+          z_in=None, resid=None, act=ACT_NONE, alpha=1.0, beta=0.0, splitk=1):
+    """C = epilogue(alpha * op(A) @ op(B)); see mi_sgemm.  A, B, C are 2-D row-major views.
+    gathers: up to three (tensor, index-or-None) pairs added row-wise."""
+    for t in (A, B, C_, bias, z_out, z_in, resid):
+        _f32(t)
+    if M is None:
+        M = A.shape[1] if transA else A.shape[0]
+    if K is None:
+        K = A.shape[0] if transA else A.shape[1]
+    if N is None:
+        N = B.shape[0] if transB else B.shape[1]
+    e = Epilogue()
+    e.bias = _p(bias)
+    g = list(gathers) + [(None, None)] * (3 - len(gathers))
+    for k, (src, idx) in enumerate(g[:3]):
+        _f32(src)
+        _i32(idx)
+        setattr(e, "g%d" % (k + 1), _p(src))
+        setattr(e, "g%d_idx" % (k + 1), _p(idx))
+        setattr(e, "g%d_ld" % (k + 1), _ld(src) if src is not None else 0)
+    e.z_out, e.z_ld = _p(z_out), (_ld(z_out) if z_out is not None else 0)
+    e.z_in, e.zin_ld = _p(z_in), (_ld(z_in) if z_in is not None else 0)
+    e.resid, e.resid_ld = _p(resid), (_ld(resid) if resid is not None else 0)
+    e.act, e.alpha, e.beta, e.splitk = act, alpha, beta, splitk
+    check(lib().mi_sgemm(int(transA), int(transB), M, N, K, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B),
+                         C_.data_ptr(), _ld(C_), C.byref(e), _stream()), "mi_sgemm")
+    return C_
+
+
+def fc_edges(node_off, edge_off, B, N, E, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
+    for t in (node_off, edge_off, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
+        _i32(t)
+    check(lib().mi_fc_edges(_p(node_off), _p(edge_off), B, N, E, _p(edge_src), _p(edge_dst), _p(edge_graph),
+                            _p(seg_ptr), _p(dst_ptr), _p(dst_perm), _p(node_graph), _stream()), "mi_fc_edges")
+
+
+def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi):
+    _f32(x), _f32(phi), _f32(cell_off), _f32(frac_diff), _i32(edge_src), _i32(edge_dst)
+    check(lib().mi_edge_fourier(_p(x), _p(edge_src), _p(edge_dst), _p(cell_off), E, F, _p(frac_diff), _p(phi),
+                                _ld(phi), _stream()), "mi_edge_fourier")
+
+
+def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False):
+    _f32(X), _f32(out), _i32(ptr), _i32(perm)
+    check(lib().mi_segment_reduce(_p(X), _ld(X), _p(ptr), _p(perm), _p(out), _ld(out), S, H, int(mean),
+                                  int(accumulate), _stream()), "mi_segment_reduce")
+    return out
+
+
+def gather_rows_dsilu(dOut, idx, ptr, z, dX, E, H):
+    _f32(dOut), _f32(z), _f32(dX), _i32(idx), _i32(ptr)
+    check(lib().mi_gather_rows_dsilu(_p(dOut), _ld(dOut), _p(idx), _p(ptr), _p(z), _ld(z) if z is not None else 0,
+                                     _p(dX), _ld(dX), E, H, _stream()), "mi_gather_rows_dsilu")
+    return dX
+
+
+def colsum(X, M, N, out, accumulate=True):
+    _f32(X), _f32(out)
+    check(lib().mi_colsum(_p(X), _ld(X), M, N, _p(out), int(accumulate), _stream()), "mi_colsum")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, y, rows, H, mean=None, rstd=None, eps=1e-5):
+    for t in (x, gamma, beta, y, mean, rstd):
+        _f32(t)
+    check(lib().mi_layernorm_fwd(_p(x), _ld(x), _p(gamma), _p(beta), _p(y), _ld(y), _p(mean), _p(rstd), rows, H,
+                                 eps, _stream()), "mi_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, H, accumulate_dx=False):
+    for t in (dy, x, gamma, mean, rstd, dx, dgamma, dbeta):
+        _f32(t)
+    check(lib().mi_layernorm_bwd(_p(dy), _ld(dy), _p(x), _ld(x), _p(gamma), _p(mean), _p(rstd), _p(dx),
+                                 _ld(dx) if dx is not None else 0, int(accumulate_dx), _p(dgamma), _p(dbeta),
+                                 rows, H, _stream()), "mi_layernorm_bwd")
+
+
+def lattice_ip(L, ips, B):
+    _f32(L), _f32(ips)
+    check(lib().mi_lattice_ip(_p(L), _p(ips), B, _stream()), "mi_lattice_ip")
+    return ips
+
+
+def bmm3(A, L, out, B, transL=False):
+    _f32(A), _f32(L), _f32(out)
+    check(lib().mi_bmm3(_p(A), _p(L), _p(out), B, int(transL), _stream()), "mi_bmm3")
+    return out
+
+
+def time_embed(t, freq, B, dim, out):
+    _i32(t), _f32(freq), _f32(out)
+    check(lib().mi_time_embed(_p(t), _p(freq), B, dim, _p(out), _stream()), "mi_time_embed")
+    return out
+
+
+def lattice_params_to_matrix(lengths, angles, L, B):
+    _f32(lengths), _f32(angles), _f32(L)
+    check(lib().mi_lattice_params_to_matrix(_p(lengths), _p(angles), _p(L), B, _stream()), "mi_lattice_params_to_matrix")
+    return L
+
+
+def lattice_matrix_to_params(L, lengths, angles, B):
+    _f32(lengths), _f32(angles), _f32(L)
+    check(lib().mi_lattice_matrix_to_params(_p(L), _p(lengths), _p(angles), B, _stream()), "mi_lattice_matrix_to_params")
+
+
+def argmax_rows(a, rows, cols, out, add=0):
+    _f32(a), _i32(out)
+    check(lib().mi_argmax_rows(_p(a), _ld(a), rows, cols, add, _p(out), _stream()), "mi_argmax_rows")
+    return out
+
+
+def reverse_corrector(x, pred_x, z_x, x_half, N, coef, t_dev=None, t_host=0):
+    for t in (x, pred_x, z_x, x_half, coef):
+        _f32(t)
+    _i32(t_dev)
+    check(lib().mi_reverse_corrector(_p(x), _p(pred_x), _p(z_x), _p(x_half), N, _p(coef), _p(t_dev), t_host,
+                                     _stream()), "mi_reverse_corrector")
+
+
+def reverse_predictor(x_half, pred_x, z_x, x, N, l, pred_l, z_l, B, a, pred_a, z_a, A, coef, t_dev=None, t_host=0):
+    for t in (x_half, pred_x, z_x, x, l, pred_l, z_l, a, pred_a, z_a, coef):
+        _f32(t)
+    _i32(t_dev)
+    check(lib().mi_reverse_predictor(_p(x_half), _p(pred_x), _p(z_x), _p(x), N, _p(l), _p(pred_l), _p(z_l), B, _p(a),
+                                     _p(pred_a), _p(z_a), A, _p(coef), _p(t_dev), t_host, _stream()),
+          "mi_reverse_predictor")
+
+
+def sampler_step_begin(t_dev, ttab, temb, B, T):
+    _i32(t_dev), _f32(ttab), _f32(temb)
+    check(lib().mi_sampler_step_begin(_p(t_dev), _p(ttab), _p(temb), B, T, _stream()), "mi_sampler_step_begin")
+
+
+def sampler_step_end(t_dev):
+    _i32(t_dev)
+    check(lib().mi_sampler_step_end(_p(t_dev), _stream()), "mi_sampler_step_end")
+
+
+def add_noise(L0, x0, Z, z_l, z_x, z_a, B, N, A, c0, c1, sigma, sigma_norm, l_t, x_t, a_t, tar_x):
+    for t in (L0, x0, z_l, z_x, z_a, l_t, x_t, a_t, tar_x):
+        _f32(t)
+    _i32(Z)
+    check(lib().mi_add_noise(_p(L0), _p(x0), _p(Z), _p(z_l), _p(z_x), _p(z_a), B, N, A, c0, c1, sigma, sigma_norm,
+                             _p(l_t), _p(x_t), _p(a_t), _p(tar_x), _stream()), "mi_add_noise")
+
+
+def rl_loss(pred, tgt, prior, node_off, B, A, costs, w_loss, w_kl, scale, loss, kl, grads):
+    """pred/tgt/prior/grads: triples (l, x, a) or None."""
+    tl, tx, ta = tgt if tgt is not None else (None, None, None)
+    ql, qx, qa = prior if prior is not None else (None, None, None)
+    dl, dx, da = grads if grads is not None else (None, None, None)
+    for t in list(pred) + [tl, tx, ta, ql, qx, qa, dl, dx, da, w_loss, w_kl, loss, kl]:
+        _f32(t)
+    _i32(node_off)
+    check(lib().mi_rl_loss(_p(pred[0]), _p(pred[1]), _p(pred[2]), _p(tl), _p(tx), _p(ta), _p(ql), _p(qx), _p(qa),
+                           _p(node_off), B, A, costs[0], costs[1], costs[2], _p(w_loss), _p(w_kl), scale, _p(loss),
+                           _p(kl), _p(dl), _p(dx), _p(da), _stream()), "mi_rl_loss")
+
+
+def adam_step(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, zero_grad=True):
+    for t in (p, g, m, v):
+        _f32(t)
+    check(lib().mi_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, b1, b2, eps, step, grad_scale,
+                             int(zero_grad), _stream()), "mi_adam_step")
+
+
+def philox_normal(out, seed, offset=0, offset_dev=None, advance=False):
+    _f32(out)
+    check(lib().mi_philox_normal(_p(out), out.numel(), seed, offset, _p(offset_dev), int(advance), _stream()),
+          "mi_philox_normal")
+    return out
+
+
+def philox_uniform(out, seed, offset=0, offset_dev=None, advance=False):
+    _f32(out)
+    check(lib().mi_philox_uniform(_p(out), out.numel(), seed, offset, _p(offset_dev), int(advance), _stream()),
+          "mi_philox_uniform")
+    return out
+
+
+def radius_graph_pbc(x, L, node_off, B, N, max_n, max_neighbors, cap, edge_dst, cell_off, deg, overflow):
+    _f32(x), _f32(L), _f32(cell_off), _i32(node_off), _i32(edge_dst), _i32(deg), _i32(overflow)
+    check(lib().mi_radius_graph_pbc(_p(x), _p(L), _p(node_off), B, N, max_n, max_neighbors, cap, _p(edge_dst), _p(cell_off),
+                                    _p(deg), _p(overflow), _stream()), "mi_radius_graph_pbc")
+
+
+def compact_edges(deg, N, cap, edge_dst_pad, cell_pad, node_graph, seg_ptr, edge_src, edge_dst, edge_graph, cell_off,
+                  E_cap):
+    check(lib().mi_compact_edges(_p(deg), N, cap, _p(edge_dst_pad), _p(cell_pad), _p(node_graph), _p(seg_ptr),
+                                 _p(edge_src), _p(edge_dst), _p(edge_graph), _p(cell_off), E_cap, _stream()),
+          "mi_compact_edges")
+
+
+def build_dst_csr(seg_ptr, edge_dst, N, E_cap, dst_ptr, dst_perm, work):
+    check(lib().mi_build_dst_csr(_p(seg_ptr), _p(edge_dst), N, E_cap, _p(dst_ptr), _p(dst_perm), _p(work), _stream()),
+          "mi_build_dst_csr")
+
+
+def replay_select(keys, rewards, n, buffer_size, cutoff, out_idx, out_count):
+    check(lib().mi_replay_select(_p(keys), _p(rewards), n, buffer_size, cutoff, _p(out_idx), _p(out_count), _stream()),
+          "mi_replay_select")
+
+
+def composition_key(Z, node_off, B, keys):
+    check(lib().mi_composition_key(_p(Z), _p(node_off), B, _p(keys), _stream()), "mi_composition_key")

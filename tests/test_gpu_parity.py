@@ -1,0 +1,198 @@
+"""GPU parity: the CUDA path against golden vectors produced by the UNMODIFIED reference
+(tests/golden/*.pt, made by oracle/make_golden.py) and against the oracle restatement.
+
+Tolerances (BASELINE.json north_star): fractional coordinates 1e-4 (wrapped distance), lattices 1e-4 rel
+(max-norm), atom-type indices bit-exact; per-crystal losses and gradients 1e-4 rel."""
+import pytest
+import torch
+
+from conftest import build_module, rel_err, wrapped_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _types(a):
+    return torch.argmax(a.detach().cpu(), dim=-1) + 1
+
+
+def _forward_case(m, case):
+    na = case["num_atoms"]
+    n2g = torch.repeat_interleave(torch.arange(len(na)), na)
+    with torch.no_grad():
+        return m.decoder(case["temb"].cuda(), case["a"].cuda(), case["x"].cuda(), case["l"].cuda(), na, n2g)
+
+
+def test_forward_small_fc(gold_small):
+    gs = gold_small
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    c = gs["forward_fc"]
+    pl, px, pt = _forward_case(m, c)
+    assert rel_err(pl, c["ref_pred_l"]) < 2e-5
+    assert rel_err(px, c["ref_pred_x"]) < 2e-5
+    assert rel_err(pt, c["ref_pred_t"]) < 2e-5
+
+
+def test_state_dict_roundtrip(gold_small):
+    gs = gold_small
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    sd = m.decoder.state_dict()
+    assert set(sd.keys()) == set(gs["sd"].keys())
+    for k, v in gs["sd"].items():
+        assert torch.equal(sd[k].cpu(), v), k
+    full = m.state_dict()
+    assert "decoder.csp_layer_0.edge_mlp.0.weight" in full and "sigma_scheduler.sigmas_norm" in full
+
+
+def test_schedules_match_reference_buffers(gold_small):
+    gs = gold_small
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    for k, v in gs["beta"].items():
+        assert torch.equal(getattr(m.beta_scheduler, k).cpu(), v), k
+    assert torch.equal(m.sigma_scheduler.sigmas.cpu(), gs["sigma_sigmas"])
+
+
+@pytest.mark.parametrize("noise_graph", [True, False])
+def test_sample_small_T40(gold_small, noise_graph):
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    gs = gold_small
+    s = gs["sample"]
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    out, traj = m.sample(make_batch(s["num_atoms"].tolist()), step_lr=s["step_lr"],
+                         noise=TapeNoise("cuda", seed=s["seed"]), use_cuda_graph=noise_graph, return_traj=True)
+    for t, ref in s["ref_traj"].items():
+        assert wrapped_err(traj[t]["frac_coords"], ref["frac_coords"]) < 1e-4, t
+        assert rel_err(traj[t]["lattices"], ref["lattices"]) < 1e-4, t
+    assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
+    assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
+    assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
+
+
+def test_sample_graph_replay_equals_eager(gold_small):
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    gs = gold_small
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    b = make_batch([5, 20, 2, 11])
+    o1, _ = m.sample(b, step_lr=5e-6, noise=TapeNoise("cuda", seed=3), use_cuda_graph=True)
+    o2, _ = m.sample(b, step_lr=5e-6, noise=TapeNoise("cuda", seed=3), use_cuda_graph=False)
+    for k in ("frac_coords", "lattices", "atom_types"):
+        assert torch.equal(o1[k], o2[k]), k
+
+
+def test_ft_timestep_gradients_small(gold_small):
+    """One inner iteration of MatInvent.ft_step (pipeline/mat_invent.py:152-164) through the plugin API with
+    torch autograd on top of the hand-written backward; every parameter gradient vs the reference's."""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    gs = gold_small
+    ft = gs["ft"]
+    agent = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    prior = build_module(gs["hp"], gs["sd_prior"], gs["sigmas_norm"])
+    for p in prior.parameters():
+        p.requires_grad = False
+    batch = make_batch(ft["num_atoms"].tolist(), **ft["crystals"])
+    batch.reward = batch.reward.cuda()
+    noised = agent.add_noise(batch, ft["t_idx"], noise=TapeNoise("cuda", seed=ft["noise_seed"]))
+    sample_loss, agent_pred = agent.calc_sample_loss(noised)
+    _, prior_pred = prior.calc_sample_loss(noised)
+    kl = agent.calc_kl_reg(agent_pred, prior_pred, batch)
+    loss = (batch.reward * sample_loss + kl * (1.1 - batch.reward) * ft["sigma"]).mean() / ft["accum"]
+    loss.backward()
+    assert rel_err(sample_loss, ft["ref_sample_loss"]) < 1e-4
+    assert rel_err(kl, ft["ref_kl"]) < 1e-4
+    assert abs(float(loss) - float(ft["ref_loss"])) < 1e-5 * abs(float(ft["ref_loss"]))
+    for k in range(3):
+        assert rel_err(agent_pred[k], ft["ref_agent_pred"][k]) < 2e-5
+        assert rel_err(prior_pred[k], ft["ref_prior_pred"][k]) < 2e-5
+    grads = agent.decoder.reference_named_grads()
+    assert set(grads.keys()) == set(gs["ft_grads"].keys())
+    worst = max((rel_err(grads[k], v), k) for k, v in gs["ft_grads"].items())
+    assert worst[0] < 1e-4, worst
+    # second backward accumulates (grad accumulation over timesteps, mat_invent.py:163-167)
+    noised = agent.add_noise(batch, ft["t_idx"], noise=TapeNoise("cuda", seed=ft["noise_seed"]))
+    sl2, ap2 = agent.calc_sample_loss(noised)
+    kl2 = agent.calc_kl_reg(ap2, prior_pred, batch)
+    ((batch.reward * sl2 + kl2 * (1.1 - batch.reward) * ft["sigma"]).mean() / ft["accum"]).backward()
+    g2 = agent.decoder.reference_named_grads()
+    worst = max((rel_err(g2[k], 2 * v), k) for k, v in gs["ft_grads"].items())
+    assert worst[0] < 1e-4, worst
+
+
+def _full_module(gold_full, which=0):
+    from oracle import diffcsp_oracle as O
+    hp = gold_full["hp"]
+    sd = O.init_params(hp, gold_full["seeds"][which])
+    cs = gold_full["checksums" if which == 0 else "checksums_prior"]
+    for k, v in sd.items():
+        assert abs(float(v.double().abs().sum()) - cs[k]) <= 1e-9 * max(1.0, cs[k]), "weight regeneration drifted: " + k
+    sn = torch.load(__import__("os").path.join(__import__("conftest").GOLD, "sigmas_norm_T1000.pt"))["sigmas_norm"]
+    return build_module(hp, sd, sn)
+
+
+def test_forward_full_size(gold_full):
+    m = _full_module(gold_full)
+    c = gold_full["forward_fc"]
+    pl, px, pt = _forward_case(m, c)
+    assert rel_err(pl, c["ref_pred_l"]) < 2e-5
+    assert rel_err(px, c["ref_pred_x"]) < 2e-5
+    assert rel_err(pt, c["ref_pred_t"]) < 2e-5
+
+
+def test_ft_gradients_full_size(gold_full):
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    ft = gold_full["ft"]
+    agent, prior = _full_module(gold_full, 0), _full_module(gold_full, 1)
+    for p in prior.parameters():
+        p.requires_grad = False
+    batch = make_batch(ft["num_atoms"].tolist(), **ft["crystals"])
+    batch.reward = batch.reward.cuda()
+    noised = agent.add_noise(batch, ft["t_idx"], noise=TapeNoise("cuda", seed=ft["noise_seed"]))
+    sample_loss, agent_pred = agent.calc_sample_loss(noised)
+    _, prior_pred = prior.calc_sample_loss(noised)
+    kl = agent.calc_kl_reg(agent_pred, prior_pred, batch)
+    ((batch.reward * sample_loss + kl * (1.1 - batch.reward) * ft["sigma"]).mean() / ft["accum"]).backward()
+    assert rel_err(sample_loss, ft["ref_sample_loss"]) < 1e-4 and rel_err(kl, ft["ref_kl"]) < 1e-4
+    grads = agent.decoder.reference_named_grads()
+    for k, chk in gold_full["ft_grad_checks"].items():
+        g = grads[k].cpu()
+        assert abs(float(g.double().abs().sum()) - chk["abs_sum"]) < 1e-4 * chk["abs_sum"] + 1e-12, k
+        scale = float(g.abs().max()) + 1e-30
+        assert float((g.reshape(-1)[:64] - chk["head"]).abs().max()) < 1e-4 * scale, k
+
+
+def test_sample_full_size_1000_steps(gold_full):
+    """The headline parity case: full-size net, 1000 reverse steps, shared noise tape."""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    s = gold_full["sample_T1000"]
+    m = _full_module(gold_full)
+    out, traj = m.sample(make_batch(s["num_atoms"].tolist()), step_lr=s["step_lr"],
+                         noise=TapeNoise("cuda", seed=s["seed"]), return_traj=True)
+    for t, ref in s["ref_traj"].items():
+        assert wrapped_err(traj[t]["frac_coords"], ref["frac_coords"]) < 1e-4, t
+        assert rel_err(traj[t]["lattices"], ref["lattices"]) < 1e-4, t
+    assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
+    assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
+    assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
+
+
+def test_generate_plugin_api(gold_small):
+    """DiffCSPSampler.generate (models/diffcsp/sample.py:148-201): shapes, ranges, post-processing vs oracle."""
+    import numpy as np
+    from oracle import diffcsp_oracle as O
+    from matinvent_b200.models.diffcsp import DiffCSPSampler
+    gs = gold_small
+    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    np.random.seed(0)
+    torch.manual_seed(0)
+    data, strucs = DiffCSPSampler(batch_size=6, num_batches=2).generate(m, filter=None, max_num=3)
+    assert len(data) == len(strucs) == 12
+    for d in data:
+        n = int(d.num_atoms)
+        assert 1 <= n <= 20 and d.frac_coords.shape == (n, 3) and d.atom_types.shape == (n,)
+        assert d.lengths.shape == (1, 3) and d.angles.shape == (1, 3)
+        assert int(d.atom_types.min()) >= 1 and int(d.atom_types.max()) <= 100
+        assert float(d.frac_coords.min()) >= 0 and float(d.frac_coords.max()) <= 1
+        assert torch.isfinite(d.lengths).all() and torch.isfinite(d.angles).all()
