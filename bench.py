@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: crystals/sec sampled with the full 1000-step reverse process (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one full pass of the hot path over one batch: the complete 1000-step predictor-corrector
+reverse diffusion (2 000 score-network evaluations) of `--batch` crystals per GPU, DiffCSP CSPNet at the
+upstream default size (hidden 512, 6 layers, 128 frequencies, fully-connected edges), synthetic
+random-init weights and mp_20 atom counts.  One JSON line is printed by rank 0.
+
+value      device-resident throughput (CUDA events, max over ranks; Philox noise generated in-graph)
+e2e        same metric through the reference-facing plugin call DiffCSPSampler.generate(): initial noise
+           drawn on the HOST and copied H2D, per-step noise from torch's device generator, results
+           post-processed and copied D2H — all inside the timed region
+roofline   dominant kernel (the per-edge GEMMs) — achieved algorithmic TFLOP/s over the measured peak
+cpu_baseline  the reference's CPU path restated in oracle/ (the reference itself cannot travel to the
+           GPU box), timed on this box's host cores on a bounded sample
+
+`--impl reference` times only that CPU path and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HP = dict(hidden_dim=512, num_layers=6, num_freqs=128, max_atoms=100, time_dim=256, latent_dim=0,
+          timesteps=1000, sigma_begin=0.005, sigma_end=0.5, costs=(1.0, 1.0, 20.0))
+STEP_LR = 5e-6
+HEAD_SCALE = 0.05          # output heads x0.05 keep random-init trajectories finite
+
+
+def atom_counts(total):
+    from matinvent_b200.models.diffcsp.sample import ATOM_DIST
+    return np.random.RandomState(0).choice(21, total, p=ATOM_DIST["mp_20"]).tolist()
+
+
+def sigmas_norm():
+    p = os.path.join(ROOT, "tests", "golden", "sigmas_norm_T1000.pt")
+    return torch.load(p)["sigmas_norm"]
+
+
+def build_model(device):
+    from matinvent_b200.models.diffcsp import DiffCSPModule
+    m = DiffCSPModule(
+        decoder=dict(hidden_dim=HP["hidden_dim"], num_layers=HP["num_layers"], max_atoms=HP["max_atoms"],
+                     num_freqs=HP["num_freqs"], edge_style="fc", cutoff=7.0, max_neighbors=20, ln=True, ip=True),
+        beta_scheduler=dict(timesteps=HP["timesteps"], scheduler_mode="cosine"),
+        sigma_scheduler=dict(timesteps=HP["timesteps"], sigma_begin=HP["sigma_begin"], sigma_end=HP["sigma_end"]),
+        cost_lattice=HP["costs"][0], cost_coord=HP["costs"][1], cost_type=HP["costs"][2],
+        time_dim=HP["time_dim"], latent_dim=HP["latent_dim"], device=device, sigmas_norm=sigmas_norm())
+    m.decoder.reset_parameters(seed=0)
+    for k in ("coord_w", "lattice_w", "type_w", "type_b"):
+        m.decoder.w(k).mul_(HEAD_SCALE)
+    return m
+
+
+def flops_per_forward(na, full_heads=True):
+    """Algorithmic FLOPs of one score-network evaluation as THIS implementation computes it
+    (split first edge linear)."""
+    H, F6, A, T, L = HP["hidden_dim"], 6 * HP["num_freqs"], HP["max_atoms"], HP["time_dim"], HP["num_layers"]
+    N, E, B = sum(na), sum(n * n for n in na), len(na)
+    edge = 2 * E * (F6 * H + H * H)
+    node = 2 * N * (H * 2 * H + 2 * H * H + H * H) + 2 * B * 9 * H
+    emb = 2 * N * (A * H + H * H) + 2 * B * T * H
+    heads = 2 * N * 3 * H + (2 * N * A * H + 2 * B * 9 * H if full_heads else 0)
+    return L * (edge + node) + emb + heads, L * edge
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 8]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm = [float(r[1]) for r in rows]
+        busy = [v for v, r in zip(sm, rows) if float(r[3]) > 300.0] or sm
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in rows)]
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=float(rows[0][2]), reasons=reasons,
+                    power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
+
+
+def cpu_reference_leg(na_all, state_dict, seconds_target=20.0, ncryst=16, steps=None):
+    """The reference's CPU path (oracle restatement of DiffCSPModule.sample, all host threads) on a bounded
+    sample: the first `ncryst` crystals of the workload, `steps` of the 1000 reverse steps; every step costs
+    the same (2 forwards), so crystals/s for 1000 steps is extrapolated linearly."""
+    from oracle import diffcsp_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    hp = O.default_hparams()
+    sch = O.Schedules(hp, sigmas_norm())
+    na = na_all[:ncryst]
+    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
+    noise = O.Noise(torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.sample(sd, hp, sch, na, noise, step_lr=STEP_LR, timesteps=2)
+        per_step = (time.perf_counter() - t0) / 2
+        if steps is None:
+            steps = int(max(4, min(200, seconds_target / max(per_step, 1e-3))))
+        t0 = time.perf_counter()
+        O.sample(sd, hp, sch, na, noise, step_lr=STEP_LR, timesteps=steps)
+        dt = time.perf_counter() - t0
+    value = len(na) / (dt / steps * HP["timesteps"])
+    return dict(value=value, unit="crystals/s", cores=cores, kind="port",
+                sample="first %d crystals of the workload, %d of 1000 reverse steps in %.1f s, extrapolated x%d"
+                       % (len(na), steps, dt, HP["timesteps"] // steps if steps else 0)), dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    na = atom_counts(args.batch)
+    from oracle import diffcsp_oracle as O
+    sd = O.init_params(O.default_hparams(), seed=0, head_scale=HEAD_SCALE)
+    vals, ms = [], []
+    total = args.warmup + args.steps
+    for i in range(total):
+        cb, per_step = cpu_reference_leg(na, sd, seconds_target=max(3.0, 60.0 / total))
+        if i >= args.warmup:
+            vals.append(cb["value"])
+            ms.append(per_step * 1e3)
+    v = float(np.mean(vals))
+    cb["value"] = v
+    print(json.dumps(dict(
+        metric="crystals/sec sampled (1000-step reverse)", value=v, unit="crystals/s", impl="reference",
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(ms)) * HP["timesteps"],
+        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload="DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU" % args.batch,
+                    note="reference CPU path (oracle port; the Python reference cannot travel to the GPU box), "
+                         "bounded sample extrapolated to 1000 steps"),
+        cpu_baseline=cb, e2e=dict(value=v, unit="crystals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="crystals per GPU (BASELINE configs[1])")
+    ap.add_argument("--timesteps", type=int, default=None, help="debug: shorter reverse process (invalid as a bench value)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from matinvent_b200 import _lib
+    from matinvent_b200.models.diffcsp import DiffCSPSampler, PhiloxNoise
+    from matinvent_b200.models.diffcsp.sample import CrystalBatch, CrystalData, postprocess
+    from matinvent_b200 import ops
+
+    m = build_model(dev)
+    T = args.timesteps or HP["timesteps"]
+    na_all = atom_counts(args.batch * world)
+    na = na_all[rank * args.batch:(rank + 1) * args.batch]          # weak scaling: fixed crystals per GPU
+    batch = CrystalBatch([CrystalData(None, None, None, None, n) for n in na])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_pass(seed):
+        out, _ = m.sample(batch, step_lr=STEP_LR, noise=PhiloxNoise(dev, seed=seed), timesteps=args.timesteps)
+        return out
+
+    for w in range(args.warmup):
+        one_pass(100 + w)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    l0 = _lib.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for k in range(args.steps):
+        out = one_pass(k)
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    clk = clocks.stop()
+    # kernels in the timed region: eager first step + one graph capture's worth per replayed step
+    g = m.decoder.graph_for(batch.num_atoms)
+    per_step_launches = None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = args.batch * world * args.steps / (ms / 1e3) * (HP["timesteps"] / T)
+    assert torch.isfinite(out["lattices"]).all() and torch.isfinite(out["frac_coords"]).all()
+
+    # ---- launches: count one eager reverse step, multiply (graph replays launch the same kernels)
+    from matinvent_b200.models.diffcsp.diffusion import _StepState
+    from matinvent_b200.models.diffcsp.scheduler import StepCoefficients
+    co = StepCoefficients(m.beta_scheduler, m.sigma_scheduler, STEP_LR)
+    st = _StepState(m, g, out["frac_coords"].clone(), out["lattices"].clone(), out["atom_types"].clone(), co, T,
+                    PhiloxNoise(dev, seed=1), False)
+    l1 = _lib.launches
+    st.step(last=False)
+    per_step_launches = _lib.launches - l1
+    gpu_launches = per_step_launches * T * args.steps
+
+    # ---- roofline of the dominant kernel: the per-edge GEMMs, CUDA events around each launch of one
+    # eager score-network evaluation on the launching stream
+    flops_fwd, flops_edge = flops_per_forward(na)
+    H, F6 = HP["hidden_dim"], 6 * HP["num_freqs"]
+    ws = m.decoder.workspace(g, False)
+    W = m.decoder.w
+    torch.cuda.synchronize()
+    evs = []
+    for rep in range(3):
+        for i in range(HP["num_layers"]):
+            q = "l%d." % i
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            ops.sgemm(ws.phi, W(q + "w_f"), ws.a1[0], M=g.E,
+                      gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
+                      act=ops.ACT_SILU)
+            e1.record()
+            ops.sgemm(ws.a1[0], W(q + "w2"), ws.a2, M=g.E, bias=W(q + "b2"), act=ops.ACT_SILU)
+            e2.record()
+            evs.append((e0, e1, e2))
+    torch.cuda.synchronize()
+    t_pair = statistics.mean(a.elapsed_time(c) for a, b, c in evs[HP["num_layers"]:]) / 1e3     # s per (GEMM1+GEMM2)
+    fl_pair = 2 * g.E * (F6 * H + H * H)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach = fl_pair / t_pair / 1e12
+    roofline = dict(bound="tensor", kernel="sgemm_kernel (per-edge GEMM pair: Phi.W_F^T + gathers + SiLU, then .W_2^T + SiLU)",
+                    achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None,
+                    peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                    note="FP32 CUDA-core FFMA path (1e-4 parity over 2000 chained forwards rules out plain TF32/BF16); "
+                         "share of step = %.2f" % (2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)))
+    # the edge-scatter (segment-mean) kernel against the HBM roofline, in isolation, L2 flushed between launches
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    seg = []
+    for rep in range(6):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.segment_reduce(ws.a2, g.seg_ptr, ws.cat[0][:, H:], g.N, H, mean=True)
+        b.record()
+        seg.append((a, b))
+    torch.cuda.synchronize()
+    t_seg = statistics.median(a.elapsed_time(b) for a, b in seg[1:]) / 1e3
+    seg_bytes = 4 * g.E * H + 4 * (g.N + 1) + 4 * g.N * H
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline_scatter = dict(bound="hbm", kernel="segment_reduce_kernel (edge scatter-mean)", achieved=seg_bytes / t_seg / 1e9,
+                            peak=hbm_peak, unit="GB/s", frac=seg_bytes / t_seg / 1e9 / hbm_peak, traffic=None,
+                            bytes_per_launch=seg_bytes, us_per_launch=t_seg * 1e6)
+
+    # ---- e2e through the plugin call, host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        sampler = DiffCSPSampler(batch_size=args.batch, num_batches=1)
+        np.random.seed(1234 + rank)
+        torch.manual_seed(1234 + rank)
+        if args.timesteps:
+            e2e = None
+        else:
+            sampler.generate(m)                         # warm (graph capture for the new atom counts)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            n_e2e = max(1, min(args.steps, 2))
+            for _ in range(n_e2e):
+                data, _ = sampler.generate(m)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nn = sum(int(d.num_atoms) for d in data)
+            e2e = dict(value=args.batch * world * n_e2e / (float(t) / 1e3), unit="crystals/s",
+                       h2d_bytes_per_step=4 * (nn * 3 + args.batch * 9 + nn * 100),
+                       d2h_bytes_per_step=4 * (nn * 3 + nn + args.batch * 6), passes=n_e2e)
+
+    cb = None
+    if rank == 0 and not args.no_cpu:
+        cb, _ = cpu_reference_leg(na_all, m.decoder.state_dict())
+
+    if rank == 0:
+        print(json.dumps(dict(
+            metric="crystals/sec sampled (1000-step reverse)", value=value, unit="crystals/s", n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload="DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU "
+                                 "(BASELINE configs[1])" % args.batch,
+                        crystals_per_gpu=args.batch, atoms_per_gpu=g.N, edges_per_gpu=g.E, reverse_steps=T,
+                        forwards_per_step=2, gflop_per_forward=flops_fwd / 1e9,
+                        l2="per-step working set (weights 49 MB + Phi %d MB + 2x edge activations %d MB) exceeds the 126 MB L2; no flush"
+                           % (4 * g.E * F6 >> 20, 2 * 4 * g.E * H >> 20),
+                        parallelism="dp%d (crystals sharded, no collective while sampling)" % world),
+            clocks=clk, gpu_launches=gpu_launches, launches_per_reverse_step=per_step_launches,
+            e2e=e2e, roofline=roofline, roofline_edge_scatter=roofline_scatter, cpu_baseline=cb)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,7 +86,14 @@ def load(path=None):
     return lib
 
 
+# kernels launched per C call (default 1); `launches` is the running total the bench reports
+KERNELS_PER_CALL = {"mi_layernorm_bwd": 2, "mi_compact_edges": 2, "mi_build_dst_csr": 4, "mi_colsum": 1}
+launches = 0
+
+
 def check(rc, what):
+    global launches
+    launches += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = _lib.mi_last_error().decode("utf-8", "replace") if _lib is not None else ""
         raise MatInventLibError("%s failed (rc=%d): %s" % (what, rc, msg))
