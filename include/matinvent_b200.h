@@ -148,23 +148,24 @@ int mi_sampler_step_end(int* t_dev, mi_stream_t stream);
 /* ---------------------------------------------------------------- forward noising + losses
  * add_noise (diffusion.py:81-119) for one integer time shared by the batch:
  *   l_t = c0*L0 + c1*z_l ; x_t = (x0 + sigma*z_x) % 1 ; a_t = c0*onehot(Z-1) + c1*z_a ;
- *   tar_x = d_log_p_wrapped_normal(sigma*z_x, sigma) / sqrt(sigma_norm)  (scheduler.py:39-43) */
+ *   tar_x = d_log_p_wrapped_normal(sigma*z_x, sigma) / sqrt(sigma_norm)  (scheduler.py:39-43)
+ * coef[t] = {sqrt(abar_t), sqrt(1-abar_t), sigma_t, sqrt(sigma_norm_t)} (device table, row = *t_dev or t_host) */
 int mi_add_noise(const float* L0, const float* x0, const int* Z, const float* z_l, const float* z_x,
-                 const float* z_a, int B, int N, int A, float c0, float c1, float sigma,
-                 float sigma_norm, float* l_t, float* x_t, float* a_t, float* tar_x,
-                 mi_stream_t stream);
+                 const float* z_a, int B, int N, int A, const float* coef, const int* t_dev, int t_host,
+                 float* l_t, float* x_t, float* a_t, float* tar_x, mi_stream_t stream);
 
 /* Per-crystal denoising loss (diffusion.py:121-138), KL proxy (diffusion.py:140-149) and the
  * reward-weighted objective of MatInvent.ft_step (pipeline/mat_invent.py:152-163), with the
  * gradient of   J = scale * sum_b [ w_loss[b]*loss_b + w_kl[b]*kl_b ]   w.r.t. the agent's
  * predictions.  prior_* may be NULL (kl = 0).  d_* may be NULL (forward only).
  * Host passes w_loss = reward, w_kl = sigma*(1.1-reward), scale = 1/(B_global*accum_steps), or the
- * upstream autograd gradient in the plugin path. */
+ * upstream autograd gradient in the plugin path.  stats (nullable, 2 floats) accumulates
+ * sum_b w_loss*loss_b and sum_b w_kl*kl_b for the ft_step logs (pipeline/mat_invent.py:168-170). */
 int mi_rl_loss(const float* pred_l, const float* pred_x, const float* pred_a, const float* tgt_l,
                const float* tgt_x, const float* tgt_a, const float* prior_l, const float* prior_x,
                const float* prior_a, const int* node_off, int B, int A, float cost_l, float cost_x,
                float cost_a, const float* w_loss, const float* w_kl, float scale, float* loss,
-               float* kl, float* d_l, float* d_x, float* d_a, mi_stream_t stream);
+               float* kl, float* d_l, float* d_x, float* d_a, float* stats, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- optimiser
  * torch.optim.Adam defaults (pipeline/mat_invent.py:136,166): flat fp32 buffers,

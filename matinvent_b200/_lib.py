@@ -46,8 +46,8 @@ PROTOTYPES = {
     "mi_reverse_predictor": [p, p, p, p, i, p, p, p, i, p, p, p, i, p, p, i, p],
     "mi_sampler_step_begin": [p, p, p, i, i, p],
     "mi_sampler_step_end": [p, p],
-    "mi_add_noise": [p, p, p, p, p, p, i, i, i, f, f, f, f, p, p, p, p, p],
-    "mi_rl_loss": [p, p, p, p, p, p, p, p, p, p, i, i, f, f, f, p, p, f, p, p, p, p, p, p],
+    "mi_add_noise": [p, p, p, p, p, p, i, i, i, p, p, i, p, p, p, p, p],
+    "mi_rl_loss": [p, p, p, p, p, p, p, p, p, p, i, i, f, f, f, p, p, f, p, p, p, p, p, p, p],
     "mi_adam_step": [p, p, p, p, ll, d, d, d, d, i, f, i, p],
     "mi_philox_normal": [p, ll, u64, u64, p, i, p],
     "mi_philox_uniform": [p, ll, u64, u64, p, i, p],

@@ -433,10 +433,12 @@ __device__ __forceinline__ float wn_score_ref(float x, float sigma) {
 __global__ void add_noise_kernel(const float* __restrict__ L0, const float* __restrict__ x0,
                                  const int* __restrict__ Z, const float* __restrict__ z_l,
                                  const float* __restrict__ z_x, const float* __restrict__ z_a, int B, int N,
-                                 int A, float c0, float c1, float sigma, float sqrt_sn,
+                                 int A, const float* __restrict__ coef, const int* __restrict__ t_dev, int t_host,
                                  float* __restrict__ l_t, float* __restrict__ x_t, float* __restrict__ a_t,
                                  float* __restrict__ tar_x) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float* cf = coef + 4 * (t_dev ? __ldg(t_dev) : t_host);     // {c0, c1, sigma, sqrt(sigma_norm)}
+    const float c0 = __ldg(cf), c1 = __ldg(cf + 1), sigma = __ldg(cf + 2), sqrt_sn = __ldg(cf + 3);
     if (i < (long long)N * A) {
         int node = (int)(i / A), k = (int)(i - (long long)node * A);
         float oh = (k == __ldg(Z + node) - 1) ? 1.f : 0.f;
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(128) rl_loss_kernel(
     const float* __restrict__ prior_l, const float* __restrict__ prior_x, const float* __restrict__ prior_a,
     const int* __restrict__ node_off, int A, float cost_l, float cost_x, float cost_a,
     const float* __restrict__ w_loss, const float* __restrict__ w_kl, float scale, float* __restrict__ loss,
-    float* __restrict__ kl, float* __restrict__ d_l, float* __restrict__ d_x, float* __restrict__ d_a) {
+    float* __restrict__ kl, float* __restrict__ d_l, float* __restrict__ d_x, float* __restrict__ d_a,
+    float* __restrict__ stats) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n0 = node_off[b], n = node_off[b + 1] - n0;
     const float wl = w_loss ? w_loss[b] * scale : 0.f;
@@ -505,7 +508,13 @@ __global__ void __launch_bounds__(128) rl_loss_kernel(
 #pragma unroll
         for (int q = 0; q < 6; ++q) t[q] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
         if (loss) loss[b] = cost_l * (t[0] / 9.f) + cost_x * (t[1] / 3.f * inv_n) + cost_a * (t[2] * inv_A * inv_n);
-        if (kl) kl[b] = t[3] / 9.f + t[4] / 3.f * inv_n + t[5] * inv_A * inv_n;
+        float klb = t[3] / 9.f + t[4] / 3.f * inv_n + t[5] * inv_A * inv_n;
+        if (kl) kl[b] = klb;
+        if (stats) {   // running sums for the ft_step logs (pipeline/mat_invent.py:168-170)
+            float lb = cost_l * (t[0] / 9.f) + cost_x * (t[1] / 3.f * inv_n) + cost_a * (t[2] * inv_A * inv_n);
+            atomicAdd(stats + 0, (w_loss ? w_loss[b] : 0.f) * lb);
+            atomicAdd(stats + 1, ((w_kl && prior_l) ? w_kl[b] : 0.f) * klb);
+        }
     }
 }
 
@@ -763,14 +772,14 @@ extern "C" int mi_sampler_step_end(int* t_dev, mi_stream_t stream) {
 }
 
 extern "C" int mi_add_noise(const float* L0, const float* x0, const int* Z, const float* z_l, const float* z_x,
-                            const float* z_a, int B, int N, int A, float c0, float c1, float sigma,
-                            float sigma_norm, float* l_t, float* x_t, float* a_t, float* tar_x, mi_stream_t stream) {
+                            const float* z_a, int B, int N, int A, const float* coef, const int* t_dev, int t_host,
+                            float* l_t, float* x_t, float* a_t, float* tar_x, mi_stream_t stream) {
     if (N <= 0 || B <= 0) return MI_OK;
-    MI_CHECK_ARG(L0 && x0 && Z && z_l && z_x && z_a && l_t && x_t && a_t && tar_x && A > 0, "null pointer");
+    MI_CHECK_ARG(L0 && x0 && Z && z_l && z_x && z_a && l_t && x_t && a_t && tar_x && A > 0 && coef, "null pointer");
     long long na = (long long)N * A;
     long long n = na > 9LL * B ? na : 9LL * B;
-    add_noise_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(L0, x0, Z, z_l, z_x, z_a, B, N, A, c0, c1, sigma,
-                                                                          sqrtf(sigma_norm), l_t, x_t, a_t, tar_x);
+    add_noise_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(L0, x0, Z, z_l, z_x, z_a, B, N, A, coef, t_dev,
+                                                                          t_host, l_t, x_t, a_t, tar_x);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -779,14 +788,14 @@ extern "C" int mi_rl_loss(const float* pred_l, const float* pred_x, const float*
                           const float* tgt_x, const float* tgt_a, const float* prior_l, const float* prior_x,
                           const float* prior_a, const int* node_off, int B, int A, float cost_l, float cost_x,
                           float cost_a, const float* w_loss, const float* w_kl, float scale, float* loss, float* kl,
-                          float* d_l, float* d_x, float* d_a, mi_stream_t stream) {
+                          float* d_l, float* d_x, float* d_a, float* stats, mi_stream_t stream) {
     if (B <= 0) return MI_OK;
     MI_CHECK_ARG(pred_l && pred_x && pred_a && node_off && A > 0, "null pointer");
     MI_CHECK_ARG((!prior_l) == (!prior_x) && (!prior_l) == (!prior_a), "prior predictions must be all set or all NULL");
     MI_CHECK_ARG((!tgt_l) == (!tgt_x) && (!tgt_l) == (!tgt_a), "targets must be all set or all NULL");
     rl_loss_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(pred_l, pred_x, pred_a, tgt_l, tgt_x, tgt_a, prior_l, prior_x, prior_a,
                                                         node_off, A, cost_l, cost_x, cost_a, w_loss, w_kl, scale, loss, kl,
-                                                        d_l, d_x, d_a);
+                                                        d_l, d_x, d_a, stats);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

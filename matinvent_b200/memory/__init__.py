@@ -1,0 +1,1 @@
+from .replay_buffer import ReplayBuffer  # noqa: F401

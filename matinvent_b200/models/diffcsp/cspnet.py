@@ -35,7 +35,7 @@ class _Workspace:
     def __init__(self, net, g, train):
         dev, f32 = g.device, torch.float32
         H, A, F6, L = net.hidden_dim, net.max_atoms, 6 * net.num_freqs, net.num_layers
-        N, E, B = g.N, g.E, g.B
+        N, E, B = g.N, getattr(g, "E_cap", g.E), g.B
         nl = L if train else 1
 
         def buf(*shape):
@@ -296,7 +296,7 @@ class CSPNet(nn.Module):
         N, E, B, L = g.N, g.E, g.B, self.num_layers
         ws = ws or self.workspace(g, train)
         if self.edge_style != "fc":
-            g.rebuild(x, l)
+            g.rebuild(x, l, need_dst=train)
             E = g.E
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
         ops.sgemm(a, W["emb_w"], ws.h0, bias=W["emb_b"], M=N)

@@ -133,6 +133,7 @@ class DiffCSPModule(nn.Module):
         if self.keep_lattice or self.keep_coords:
             raise NotImplementedError("keep_lattice / keep_coords (zero lattice/coord cost) is not part of the MatInvent path")
         self._time_table = None
+        self._noise_table = None
         self._step_graphs = {}
         self.to(dev)
 
@@ -151,9 +152,19 @@ class DiffCSPModule(nn.Module):
             self._time_table = time_embedding_table(self.timesteps, self.time_dim).to(self.device)
         return self._time_table
 
+    def noise_table(self):
+        """[T+1, 4] rows {sqrt(abar_t), sqrt(1-abar_t), sigma_t, sqrt(sigma_norm_t)} of add_noise (diffusion.py:91-98)."""
+        if self._noise_table is None or self._noise_table.device != self.device:
+            ac = self.beta_scheduler.alphas_cumprod.cpu()
+            cols = [torch.sqrt(ac), torch.sqrt(1.0 - ac), self.sigma_scheduler.sigmas.cpu(),
+                    torch.sqrt(self.sigma_scheduler.sigmas_norm.cpu())]
+            self._noise_table = torch.stack(cols, dim=1).contiguous().to(self.device)
+        return self._noise_table
+
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
         self._time_table = None
+        self._noise_table = None
         self._step_graphs = {}
         return r
 
@@ -176,12 +187,9 @@ class DiffCSPModule(nn.Module):
         z_l = noise.step_randn((B, 3, 3))
         z_x = noise.step_randn((N, 3))
         z_a = noise.step_randn((N, A))
-        ac = self.beta_scheduler.alphas_cumprod[t]
-        c0, c1 = float(torch.sqrt(ac)), float(torch.sqrt(1.0 - ac))
-        sigma, sn = float(self.sigma_scheduler.sigmas[t]), float(self.sigma_scheduler.sigmas_norm[t])
         l_t, x_t = torch.empty(B, 3, 3, device=dev), torch.empty(N, 3, device=dev)
         a_t, tar_x = torch.empty(N, A, device=dev), torch.empty(N, 3, device=dev)
-        ops.add_noise(db.L0, db.x0, db.Z, z_l, z_x, z_a, B, N, A, c0, c1, sigma, sn, l_t, x_t, a_t, tar_x)
+        ops.add_noise(db.L0, db.x0, db.Z, z_l, z_x, z_a, B, N, A, self.noise_table(), l_t, x_t, a_t, tar_x, t_host=t)
         temb = self.time_table()[t].expand(B, -1).contiguous()
         noised_input = (temb, a_t, x_t, l_t, g.num_atoms, g.node2graph)
         return noised_input, (z_l, tar_x, z_a), g.node2graph

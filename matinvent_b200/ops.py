@@ -186,25 +186,25 @@ def sampler_step_end(t_dev):
     check(lib().mi_sampler_step_end(_p(t_dev), _stream()), "mi_sampler_step_end")
 
 
-def add_noise(L0, x0, Z, z_l, z_x, z_a, B, N, A, c0, c1, sigma, sigma_norm, l_t, x_t, a_t, tar_x):
-    for t in (L0, x0, z_l, z_x, z_a, l_t, x_t, a_t, tar_x):
+def add_noise(L0, x0, Z, z_l, z_x, z_a, B, N, A, coef, l_t, x_t, a_t, tar_x, t_dev=None, t_host=0):
+    for t in (L0, x0, z_l, z_x, z_a, l_t, x_t, a_t, tar_x, coef):
         _f32(t)
-    _i32(Z)
-    check(lib().mi_add_noise(_p(L0), _p(x0), _p(Z), _p(z_l), _p(z_x), _p(z_a), B, N, A, c0, c1, sigma, sigma_norm,
+    _i32(Z), _i32(t_dev)
+    check(lib().mi_add_noise(_p(L0), _p(x0), _p(Z), _p(z_l), _p(z_x), _p(z_a), B, N, A, _p(coef), _p(t_dev), t_host,
                              _p(l_t), _p(x_t), _p(a_t), _p(tar_x), _stream()), "mi_add_noise")
 
 
-def rl_loss(pred, tgt, prior, node_off, B, A, costs, w_loss, w_kl, scale, loss, kl, grads):
+def rl_loss(pred, tgt, prior, node_off, B, A, costs, w_loss, w_kl, scale, loss, kl, grads, stats=None):
     """pred/tgt/prior/grads: triples (l, x, a) or None."""
     tl, tx, ta = tgt if tgt is not None else (None, None, None)
     ql, qx, qa = prior if prior is not None else (None, None, None)
     dl, dx, da = grads if grads is not None else (None, None, None)
-    for t in list(pred) + [tl, tx, ta, ql, qx, qa, dl, dx, da, w_loss, w_kl, loss, kl]:
+    for t in list(pred) + [tl, tx, ta, ql, qx, qa, dl, dx, da, w_loss, w_kl, loss, kl, stats]:
         _f32(t)
     _i32(node_off)
     check(lib().mi_rl_loss(_p(pred[0]), _p(pred[1]), _p(pred[2]), _p(tl), _p(tx), _p(ta), _p(ql), _p(qx), _p(qa),
                            _p(node_off), B, A, costs[0], costs[1], costs[2], _p(w_loss), _p(w_kl), scale, _p(loss),
-                           _p(kl), _p(dl), _p(dx), _p(da), _stream()), "mi_rl_loss")
+                           _p(kl), _p(dl), _p(dx), _p(da), _p(stats), _stream()), "mi_rl_loss")
 
 
 def adam_step(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0, zero_grad=True):
