@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcuda"]
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs
     subprocess.check_call(cmd)
     with open(stamp, "w") as fh:
         fh.write(dig)

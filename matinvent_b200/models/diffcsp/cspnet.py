@@ -119,6 +119,11 @@ class CSPNet(nn.Module):
         self._flat_grad = None
         self._ws = {}
         self._graphs = {}
+        # tensor-core path (mi_tc_gemm): TF32 head / tail of every weight, refreshed when the weights change
+        self.use_tc = True
+        self._flat_hi = self._flat_lo = None
+        self._hi, self._lo = {}, {}
+        self._tc_version = None
         self.reset_parameters()
 
     # ------------------------------------------------------------------ parameters
@@ -135,13 +140,41 @@ class CSPNet(nn.Module):
         self._gviews = {}
         self._rebuild_views()
         self._ws, self._graphs = {}, {}
+        self._flat_hi = self._flat_lo = None
+        self._tc_version = None
         return r
+
+    def weights_changed(self):
+        """Call after the flat weight buffer was written outside torch (mi_adam_step): the TF32 split copies
+        used by the tensor-core GEMMs are rebuilt on the next forward."""
+        self._tc_version = None
+        if self.use_tc and self._flat_hi is not None:
+            self._refresh_tc()          # immediately: captured CUDA graphs read the split copies
+
+    def _refresh_tc(self):
+        ver = self.flat._version
+        if self._tc_version == ver and self._flat_hi is not None:
+            return
+        if self._flat_hi is None:
+            self._flat_hi, self._flat_lo = torch.empty_like(self.flat.data), torch.empty_like(self.flat.data)
+            self._hi = {k: self._flat_hi[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
+            self._lo = {k: self._flat_lo[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
+        ops.tf32_split(self.flat.data, self._flat_hi, self._flat_lo)
+        self._tc_version = ver
+
+    def _linear(self, A, wname, C, M, **epi):
+        """C = epilogue(A @ W^T): tensor cores (3xTF32) when the operands are TMA-compatible, else FP32 FFMA."""
+        W = self._views[wname]
+        if self.use_tc and ops.tc_ok(A, W):
+            return ops.tc_gemm(A, self._hi[wname], self._lo[wname], C, M=M, **epi)
+        return ops.sgemm(A, W, C, M=M, **epi)
 
     @property
     def device(self):
         return self.flat.device
 
     def w(self, name):
+        """Native weight block (a view into the flat buffer).  After writing to it call weights_changed()."""
         return self._views[name]
 
     def flat_grad(self):
@@ -223,6 +256,7 @@ class CSPNet(nn.Module):
         else:
             v["fin_g"].fill_(1.0), v["fin_b"].zero_()
         put(v["type_w"], g("type_out.weight")), put(v["type_b"], g("type_out.bias"))
+        self.weights_changed()
 
     def _reference_named(self, views):
         """Inverse of _load_reference_state: reference-named tensors from native blocks."""
@@ -298,10 +332,12 @@ class CSPNet(nn.Module):
         if self.edge_style != "fc":
             g.rebuild(x, l, need_dst=train)
             E = g.E
+        if self.use_tc:
+            self._refresh_tc()
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
-        ops.sgemm(a, W["emb_w"], ws.h0, bias=W["emb_b"], M=N)
-        ops.sgemm(temb, W["lat_w_t"], ws.tb, bias=W["lat_b"], M=B)
-        ops.sgemm(ws.h0, W["lat_w_h"], ws.h[0], gathers=[(ws.tb, g.node_graph)], M=N)
+        self._linear(a, "emb_w", ws.h0, N, bias=W["emb_b"])
+        self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
+        self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)])
         ops.lattice_ip(l, ws.ips, B)
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi)
         for i in range(L):
@@ -316,18 +352,18 @@ class CSPNet(nn.Module):
             else:
                 hn.copy_(h_in)
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
-            ops.sgemm(hn, W[q + "w_pq"], ws.pq, M=N)
-            ops.sgemm(ws.ips, W[q + "w_l"], ws.cb, bias=W[q + "b1"], M=B)
-            ops.sgemm(ws.phi, W[q + "w_f"], a1, M=E,
-                      gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
-                      z_out=ws.z1[i] if train else None, act=ACT_SILU)
-            ops.sgemm(a1, W[q + "w2"], ws.a2, M=E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU)
+            self._linear(hn, q + "w_pq", ws.pq, N)
+            self._linear(ws.ips, q + "w_l", ws.cb, B, bias=W[q + "b1"])
+            self._linear(ws.phi, q + "w_f", a1, E,
+                         gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
+                         z_out=ws.z1[i] if train else None, act=ACT_SILU)
+            self._linear(a1, q + "w2", ws.a2, E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU)
             # scatter-mean over the source node (cspnet.py:79)
             ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True)
             # node model + residual (cspnet.py:77-91)
-            ops.sgemm(cat, W[q + "wn1"], an1, M=N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU)
-            ops.sgemm(an1, W[q + "wn2"], h_out, M=N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
-                      act=ACT_SILU, resid=h_in)
+            self._linear(cat, q + "wn1", an1, N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU)
+            self._linear(an1, q + "wn2", h_out, N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
+                         act=ACT_SILU, resid=h_in)
         hL = ws.h[L]
         if self.ln:
             ops.layernorm_fwd(hL, W["fin_g"], W["fin_b"], ws.hf, N, H,
@@ -337,16 +373,16 @@ class CSPNet(nn.Module):
             hf = hL
         ws.hf_used = hf
         if heads[1]:
-            ops.sgemm(hf, W["coord_w"], ws.pred_x, M=N)
+            self._linear(hf, "coord_w", ws.pred_x, N)
         if heads[0]:
             ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True)
             if self.ip:
-                ops.sgemm(ws.gmean, W["lattice_w"], ws.lat9, M=B)
+                self._linear(ws.gmean, "lattice_w", ws.lat9, B)
                 ops.bmm3(ws.lat9, l, ws.pred_l, B)
             else:
-                ops.sgemm(ws.gmean, W["lattice_w"], ws.pred_l.view(B, 9), M=B)
+                self._linear(ws.gmean, "lattice_w", ws.pred_l.view(B, 9), B)
         if heads[2]:
-            ops.sgemm(hf, W["type_w"], ws.pred_a, bias=W["type_b"], M=N)
+            self._linear(hf, "type_w", ws.pred_a, N, bias=W["type_b"])
         return ws.pred_l, ws.pred_x, ws.pred_a
 
     # ------------------------------------------------------------------ backward

@@ -168,6 +168,7 @@ class FineTuner:
             dist.all_reduce(self.grad, group=self.pg)
         self.adam_t += 1
         ops.adam_step(self.agent.decoder.flat.data, self.grad, self.m, self.v, self.lr, self.adam_t, zero_grad=True)
+        self.agent.decoder.weights_changed()
 
 
 class _LocalBatch:

@@ -53,6 +53,7 @@ class DiffCSPSuite(ModelSuite):
             if scale != 1.0:
                 for k in ("coord_w", "lattice_w", "type_w", "type_b"):
                     model.decoder.w(k).mul_(scale)
+                model.decoder.weights_changed()
         else:
             model_path = os.path.abspath(self.model_path)
             cfg = Config.load(os.path.join(model_path, "hparams.yaml"))

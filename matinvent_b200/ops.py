@@ -75,6 +75,47 @@ def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None
     return C_
 
 
+def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk):
+    e = Epilogue()
+    e.bias = _p(bias)
+    g = list(gathers) + [(None, None)] * (3 - len(gathers))
+    for k, (src, idx) in enumerate(g[:3]):
+        _f32(src)
+        _i32(idx)
+        setattr(e, "g%d" % (k + 1), _p(src))
+        setattr(e, "g%d_idx" % (k + 1), _p(idx))
+        setattr(e, "g%d_ld" % (k + 1), _ld(src) if src is not None else 0)
+    e.z_out, e.z_ld = _p(z_out), (_ld(z_out) if z_out is not None else 0)
+    e.z_in, e.zin_ld = _p(z_in), (_ld(z_in) if z_in is not None else 0)
+    e.resid, e.resid_ld = _p(resid), (_ld(resid) if resid is not None else 0)
+    e.act, e.alpha, e.beta, e.splitk = act, alpha, beta, splitk
+    return e
+
+
+def tf32_split(w, hi, lo):
+    _f32(w), _f32(hi), _f32(lo)
+    check(lib().mi_tf32_split(_p(w), _p(hi), _p(lo), w.numel(), _stream()), "mi_tf32_split")
+
+
+def tc_ok(A, W):
+    """operands usable by the TMA / tcgen05 path: 16-byte aligned rows"""
+    return (_ld(A) % 4 == 0 and _ld(W) % 4 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
+
+
+def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
+            act=ACT_NONE, alpha=1.0, beta=0.0):
+    """C = epilogue(alpha * A @ W^T) on the tensor cores (3xTF32); W_hi/W_lo from tf32_split.  See mi_tc_gemm."""
+    for t in (A, W_hi, W_lo, C_, bias, z_out, z_in, resid):
+        _f32(t)
+    M = A.shape[0] if M is None else M
+    K = A.shape[1] if K is None else K
+    N = W_hi.shape[0] if N is None else N
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1)
+    check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
+                           _ld(C_), C.byref(e), _stream()), "mi_tc_gemm")
+    return C_
+
+
 def fc_edges(node_off, edge_off, B, N, E, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
     for t in (node_off, edge_off, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
         _i32(t)

@@ -173,6 +173,23 @@ def test_sample_full_size_1000_steps(gold_full):
     for t, ref in s["ref_traj"].items():
         assert wrapped_err(traj[t]["frac_coords"], ref["frac_coords"]) < 1e-4, t
         assert rel_err(traj[t]["lattices"], ref["lattices"]) < 1e-4, t
+    print("1000-step parity: frac %.2e  lattice %.2e" % (wrapped_err(out["frac_coords"], s["ref_frac_coords"]),
+                                                         rel_err(out["lattices"], s["ref_lattices"])))
+    assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
+    assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
+    assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
+
+
+def test_sample_full_size_1000_steps_ffma_path(gold_full):
+    """Same case with the tensor-core GEMMs disabled (FP32 CUDA-core path) — kept as the accuracy yardstick."""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    s = gold_full["sample_T1000"]
+    m = _full_module(gold_full)
+    m.decoder.use_tc = False
+    out, _ = m.sample(make_batch(s["num_atoms"].tolist()), step_lr=s["step_lr"], noise=TapeNoise("cuda", seed=s["seed"]))
+    print("1000-step parity (FFMA): frac %.2e  lattice %.2e" % (wrapped_err(out["frac_coords"], s["ref_frac_coords"]),
+                                                                rel_err(out["lattices"], s["ref_lattices"])))
     assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
     assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
     assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
