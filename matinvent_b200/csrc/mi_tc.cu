@@ -16,19 +16,26 @@
 // Shared memory: 2 stages x (A_hi 16K | A_lo 16K | W_hi 32K | W_lo 32K) = 192 KB, 128B-swizzled K-major tiles
 // (TMA SWIZZLE_128B <-> UMMA SWIZZLE_128B descriptors), BK = 32 floats = one 128-byte swizzle row.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "mi_common.cuh"
 
 namespace {
 
-constexpr int TM = 128, TN = 256, TK = 32;          // CTA tile; TK floats = 128 bytes
-constexpr int STAGES = 2;
-constexpr int A_BYTES = TM * TK * 4;                // 16 KB
-constexpr int W_BYTES = TN * TK * 4;                // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // 96 KB
-constexpr int TC_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TM = 128, TN = 256;                   // CTA tile
+constexpr int TC_THREADS = 320;   // w0 TMA, w1 MMA, w2..5 split + epilogue, w6..9 epilogue only
+// Pipeline shape: TK floats per k-block (32 -> 128-byte swizzle rows, 16 -> 64-byte), STAGES stages;
+// both variants use 192 KB: {32, 2} = 2 x 96 KB, {16, 4} = 4 x 48 KB (deeper prefetch, same bytes per flop).
+template <int TK, int STAGES>
+struct Cfg {
+    static constexpr int A_BYTES = TM * TK * 4;
+    static constexpr int W_BYTES = TN * TK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint64_t SBO = (8 * TK * 4) >> 4;            // 8-row group pitch, 16-byte units
+    static constexpr uint64_t LAYOUT = (TK == 32) ? 2 : 4;        // UMMA SWIZZLE_128B / SWIZZLE_64B
+};
 constexpr uint32_t TMEM_COLS = 512;   // [0,256): a_hi.w_hi ; [256,512): a_lo.w_hi + a_hi.w_lo (summed in the epilogue)
 
 // tcgen05 instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2),
@@ -66,13 +73,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 // K-major, 128B-swizzled operand tile: 8-row groups of 1024 B (SBO), LBO unused (=1), version 1, layout 2.
+template <class C>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= C::SBO << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= C::LAYOUT << 61;
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -88,6 +96,9 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// SiLU with ex2/rcp approximations (~3e-7 relative, below the GEMM's own error): 5 instructions instead of ~25,
+// the epilogue is issue/latency bound otherwise.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 struct TcParams {
@@ -97,9 +108,12 @@ struct TcParams {
     int c_vec;
 };
 
+template <int TK, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+    using C = Cfg<TK, STAGES>;
+    constexpr int A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -155,8 +169,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&split[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + A_BYTES);
-                const uint64_t d_whi = umma_desc(st + 2 * A_BYTES), d_wlo = umma_desc(st + 2 * A_BYTES + W_BYTES);
+                const uint64_t d_ahi = umma_desc<C>(st), d_alo = umma_desc<C>(st + A_BYTES);
+                const uint64_t d_whi = umma_desc<C>(st + 2 * A_BYTES), d_wlo = umma_desc<C>(st + 2 * A_BYTES + W_BYTES);
 #pragma unroll
                 for (int k = 0; k < TK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 8 tf32 = 32 bytes along the swizzle row
@@ -173,8 +187,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
     } else {
         // ===================== split warpgroup (then epilogue) =====================
-        const int t = threadIdx.x - 64;     // 0..127
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int t = threadIdx.x - 64;     // 0..127 for the split warps
+        for (int kb = 0; kb < nkb && warp < 6; ++kb) {
             const int s = kb % STAGES;
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(&full[s], ph);
@@ -203,7 +217,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float* g1r = (row_ok && e.g1) ? e.g1 + (long long)(e.g1_idx ? __ldg(e.g1_idx + m) : m) * e.g1_ld : nullptr;
         const float* g2r = (row_ok && e.g2) ? e.g2 + (long long)(e.g2_idx ? __ldg(e.g2_idx + m) : m) * e.g2_ld : nullptr;
         const float* g3r = (row_ok && e.g3) ? e.g3 + (long long)(e.g3_idx ? __ldg(e.g3_idx + m) : m) * e.g3_ld : nullptr;
-        for (int c = 0; c < TN / 32; ++c) {
+        const int hf = (warp - 2) >> 2;             // column half handled by this warp
+        for (int c = hf * (TN / 64); c < (hf + 1) * (TN / 64); ++c) {
             const int nb = n0 + c * 32;
             if (nb >= p.N) break;                    // warp-uniform
             uint32_t v[32], w[32];
@@ -246,7 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (e.z_out) *reinterpret_cast<float4*>(e.z_out + (long long)m * e.z_ld + n) = make_float4(x[0], x[1], x[2], x[3]);
                     if (e.act == MI_ACT_SILU) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) x[u] = mi_silu(x[u]);
+                        for (int u = 0; u < 4; ++u) x[u] = silu_fast(x[u]);
                     } else if (e.act == MI_ACT_DSILU) {
                         float4 tq = __ldg(reinterpret_cast<const float4*>(e.z_in + (long long)m * e.zin_ld + n));
                         x[0] *= mi_dsilu(tq.x); x[1] *= mi_dsilu(tq.y); x[2] *= mi_dsilu(tq.z); x[3] *= mi_dsilu(tq.w);
@@ -266,7 +281,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (g3r) x += __ldg(g3r + n);
                     if (e.beta != 0.f) x += e.beta * crow[j];
                     if (e.z_out) e.z_out[(long long)m * e.z_ld + n] = x;
-                    if (e.act == MI_ACT_SILU) x = mi_silu(x);
+                    if (e.act == MI_ACT_SILU) x = silu_fast(x);
                     else if (e.act == MI_ACT_DSILU) x *= mi_dsilu(__ldg(e.z_in + (long long)m * e.zin_ld + n));
                     if (e.resid) x += __ldg(e.resid + (long long)m * e.resid_ld + n);
                     crow[j] = x;
@@ -307,13 +322,14 @@ int get_encode() {
 }
 
 // 2-D fp32 row-major [rows, cols] (ld elements between rows), box = [box_rows, 32 cols], 128B swizzle, zero OOB fill
-int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows, int tk) {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)tk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, tk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         mi_set_error_("cuTensorMapEncodeTiled failed (%d) for [%lld,%lld] ld %lld", (int)r, rows, cols, ld);
@@ -322,7 +338,19 @@ int make_map(CUtensorMap* map, const float* base, long long rows, long long cols
     return MI_OK;
 }
 
-bool g_attr_set = false;
+int g_variant = -1;   // MI_TC_VARIANT env: 0 = {TK 32, 2 stages}, 1 = {TK 16, 4 stages} (default)
+
+template <int TK, int STAGES>
+int launch_tc(dim3 grid, cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p) {
+    static bool attr = false;
+    if (!attr) {
+        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TK, STAGES>::SMEM_BYTES));
+        attr = true;
+    }
+    tc_gemm_kernel<TK, STAGES><<<grid, TC_THREADS, Cfg<TK, STAGES>::SMEM_BYTES, s>>>(mA, mWh, mWl, p);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
 
 }  // namespace
 
@@ -364,17 +392,17 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const fl
     if (e.z_in) cv = cv && (e.zin_ld % 4 == 0) && mi_host_aligned16(e.z_in);
     if (e.resid) cv = cv && (e.resid_ld % 4 == 0) && mi_host_aligned16(e.resid);
     p.c_vec = cv;
-    CUtensorMap mA, mWh, mWl;
-    if ((rc = make_map(&mA, A, M, K, lda, TM)) != MI_OK) return rc;
-    if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN)) != MI_OK) return rc;
-    if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN)) != MI_OK) return rc;
-    if (!g_attr_set) {
-        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        g_attr_set = true;
+    if (g_variant < 0) {
+        const char* v = getenv("MI_TC_VARIANT");
+        g_variant = v ? atoi(v) : 1;
     }
+    const int tk = g_variant == 0 ? 32 : 16;
+    CUtensorMap mA, mWh, mWl;
+    if ((rc = make_map(&mA, A, M, K, lda, TM, tk)) != MI_OK) return rc;
+    if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, tk)) != MI_OK) return rc;
+    if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, tk)) != MI_OK) return rc;
     dim3 grid(mi_div_up(N, TN), mi_div_up(M, TM));
     MI_CHECK_ARG(grid.y <= 65535u, "grid too large");
-    tc_gemm_kernel<<<grid, TC_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mA, mWh, mWl, p);
-    MI_CHECK_LAUNCH();
-    return MI_OK;
+    if (g_variant == 0) return launch_tc<32, 2>(grid, (cudaStream_t)stream, mA, mWh, mWl, p);
+    return launch_tc<16, 4>(grid, (cudaStream_t)stream, mA, mWh, mWl, p);
 }

@@ -56,7 +56,7 @@ def test_tc_gemm_fused_epilogue_and_views():
     ops.tc_gemm(A, hi, lo, C, bias=bias, gathers=[(P[:, :N], i1), (Q, i2), (Cb, i3)], z_out=Z, act=ops.ACT_SILU, resid=R)
     z = A.double() @ W.double().t() + bias.double() + P.double()[i1.long(), :N] + Q.double()[i2.long()] + Cb.double()[i3.long()]
     assert rel_err(Z, z) < 3e-6
-    assert rel_err(C, torch.nn.functional.silu(z) + R.double()) < 3e-6
+    assert rel_err(C, torch.nn.functional.silu(z) + R.double()) < 5e-6     # + ex2/rcp-approx SiLU (~3e-7)
     assert float(out[:, :N].abs().max()) == 0.0
 
 
