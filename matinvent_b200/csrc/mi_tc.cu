@@ -23,25 +23,23 @@
 
 namespace {
 
-constexpr int TM = 128, TN = 256;                   // CTA tile
+constexpr int TM = 128;                              // CTA tile rows; columns TN in {256, 128, 64} (template)
 constexpr int TC_THREADS = 320;   // w0 TMA, w1 MMA, w2..5 split + epilogue, w6..9 epilogue only
 // Pipeline shape: TK floats per k-block (32 -> 128-byte swizzle rows, 16 -> 64-byte), STAGES stages;
 // both variants use 192 KB: {32, 2} = 2 x 96 KB, {16, 4} = 4 x 48 KB (deeper prefetch, same bytes per flop).
-template <int TK, int STAGES>
+template <int TK, int STAGES, int TN>
 struct Cfg {
     static constexpr int A_BYTES = TM * TK * 4;
     static constexpr int W_BYTES = TN * TK * 4;
+    static constexpr uint32_t TMEM_COLS = 2 * TN;                 // main + correction accumulators
+    // tcgen05 instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2),
+    // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr uint64_t SBO = (8 * TK * 4) >> 4;            // 8-row group pitch, 16-byte units
     static constexpr uint64_t LAYOUT = (TK == 32) ? 2 : 4;        // UMMA SWIZZLE_128B / SWIZZLE_64B
 };
-constexpr uint32_t TMEM_COLS = 512;   // [0,256): a_hi.w_hi ; [256,512): a_lo.w_hi + a_hi.w_lo (summed in the epilogue)
-
-// tcgen05 instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2),
-// both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -83,14 +81,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     d |= C::LAYOUT << 61;
     return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -108,11 +106,12 @@ struct TcParams {
     int c_vec;
 };
 
-template <int TK, int STAGES>
+template <int TK, int STAGES, int TN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
-    using C = Cfg<TK, STAGES>;
+    using C = Cfg<TK, STAGES, TN>;
+    constexpr uint32_t TMEM_COLS = C::TMEM_COLS, IDESC = C::IDESC;
     constexpr int A_BYTES = C::A_BYTES, W_BYTES = C::W_BYTES, STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -177,9 +176,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     // the tensor core truncates when it adds into the accumulator, so the error grows with the
                     // number of accumulating instructions: keep the 2^-11-sized correction terms out of the
                     // main accumulator (their truncation errors are 2^-11 smaller in their own accumulator)
-                    umma_tf32(tmem_base, d_ahi + adv, d_whi + adv, (kb | k) != 0);
-                    umma_tf32(tmem_base + TN, d_alo + adv, d_whi + adv, (kb | k) != 0);
-                    umma_tf32(tmem_base + TN, d_ahi + adv, d_wlo + adv, 1u);
+                    umma_tf32(tmem_base, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
+                    umma_tf32(tmem_base + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
+                    umma_tf32(tmem_base + TN, d_ahi + adv, d_wlo + adv, IDESC, 1u);
                 }
                 umma_commit(&empty[s]);
             }
@@ -218,7 +217,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float* g2r = (row_ok && e.g2) ? e.g2 + (long long)(e.g2_idx ? __ldg(e.g2_idx + m) : m) * e.g2_ld : nullptr;
         const float* g3r = (row_ok && e.g3) ? e.g3 + (long long)(e.g3_idx ? __ldg(e.g3_idx + m) : m) * e.g3_ld : nullptr;
         const int hf = (warp - 2) >> 2;             // column half handled by this warp
-        for (int c = hf * (TN / 64); c < (hf + 1) * (TN / 64); ++c) {
+        for (int c = hf * (TN / 64); c < (hf + 1) * (TN / 64); ++c) {   // TN/32 column chunks, half per warp set
             const int nb = n0 + c * 32;
             if (nb >= p.N) break;                    // warp-uniform
             uint32_t v[32], w[32];
@@ -340,14 +339,23 @@ int make_map(CUtensorMap* map, const float* base, long long rows, long long cols
 
 int g_variant = -1;   // MI_TC_VARIANT env: 0 = {TK 32, 2 stages}, 1 = {TK 16, 4 stages} (default)
 
-template <int TK, int STAGES>
-int launch_tc(dim3 grid, cudaStream_t s, const CUtensorMap& mA, const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p) {
+template <int TK, int STAGES, int TN>
+int launch_tc(int M, int N, int K, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, cudaStream_t s,
+              const TcParams& p) {
+    using C = Cfg<TK, STAGES, TN>;
     static bool attr = false;
+    int rc;
+    CUtensorMap mA, mWh, mWl;
+    if ((rc = make_map(&mA, A, M, K, lda, TM, TK)) != MI_OK) return rc;
+    if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, TK)) != MI_OK) return rc;
+    if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, TK)) != MI_OK) return rc;
     if (!attr) {
-        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<TK, STAGES>::SMEM_BYTES));
+        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TK, STAGES, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
-    tc_gemm_kernel<TK, STAGES><<<grid, TC_THREADS, Cfg<TK, STAGES>::SMEM_BYTES, s>>>(mA, mWh, mWl, p);
+    dim3 grid(mi_div_up(N, TN), mi_div_up(M, TM));
+    MI_CHECK_ARG(grid.y <= 65535u, "grid too large");
+    tc_gemm_kernel<TK, STAGES, TN><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mWh, mWl, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -396,13 +404,18 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const fl
         const char* v = getenv("MI_TC_VARIANT");
         g_variant = v ? atoi(v) : 1;
     }
-    const int tk = g_variant == 0 ? 32 : 16;
-    CUtensorMap mA, mWh, mWl;
-    if ((rc = make_map(&mA, A, M, K, lda, TM, tk)) != MI_OK) return rc;
-    if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, tk)) != MI_OK) return rc;
-    if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, tk)) != MI_OK) return rc;
-    dim3 grid(mi_div_up(N, TN), mi_div_up(M, TM));
-    MI_CHECK_ARG(grid.y <= 65535u, "grid too large");
-    if (g_variant == 0) return launch_tc<32, 2>(grid, (cudaStream_t)stream, mA, mWh, mWl, p);
-    return launch_tc<16, 4>(grid, (cudaStream_t)stream, mA, mWh, mWl, p);
+    // Column-tile width: small-M node GEMMs and the per-GPU shards of an 8-GPU run leave most SMs idle with
+    // 128x256 tiles.
+    const long long mt = mi_div_up(M, TM);
+    int tn = 256;                                  // measured on B200: 128x128 tiles win below ~half a wave of 128x256 tiles
+    if (mt * mi_div_up(N, 256) < 74) tn = 128;
+    if (N <= 64) tn = 64;
+    else if (N <= 128) tn = 128;
+    const char* force = getenv("MI_TC_TN");
+    if (force) tn = atoi(force);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_variant == 0 && tn == 256) return launch_tc<32, 2, 256>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);
+    if (tn == 256) return launch_tc<16, 4, 256>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);
+    if (tn == 128) return launch_tc<32, 3, 128>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);
+    return launch_tc<32, 4, 64>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);
 }
