@@ -66,12 +66,13 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
              int ldb, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
 
 /* Tensor-core variant for the forward dense blocks (A [M,K] and W [N,K] both K-contiguous, i.e.
- * transA = 0, transB = 1): FP32-grade product by 3xTF32 split precision on tcgen05 (TMA-staged 128B-swizzled
- * operand tiles, TMEM accumulator), same epilogue contract as mi_sgemm (no split-K).  W_hi / W_lo are the
- * TF32 head and tail of the weight, produced by mi_tf32_split (elementwise, once per weight update).
- * Requires lda, ldw multiples of 4 and 16-byte aligned A, W_hi, W_lo. */
-int mi_tf32_split(const float* w, float* hi, float* lo, long long n, mi_stream_t stream);
-int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw,
+ * transA = 0, transB = 1): FP32-grade product by split-precision FP16 on tcgen05 (x = x_hi + 2^-11 x_lo, three
+ * MMAs per k-slice, TMA-staged swizzled operand tiles, two TMEM accumulators), same epilogue contract as
+ * mi_sgemm (no split-K).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
+ * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo,
+ * and |values| < 65504. */
+int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_stream_t stream);
+int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
                float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- graph construction

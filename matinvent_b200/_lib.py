@@ -29,7 +29,7 @@ PROTOTYPES = {
     "mi_version": [],
     "mi_device_info": [C.POINTER(i), C.POINTER(i), C.POINTER(i)],
     "mi_sgemm": [i, i, i, i, i, p, i, p, i, p, i, C.POINTER(Epilogue), p],
-    "mi_tf32_split": [p, p, p, ll, p],
+    "mi_f16_split": [p, p, p, ll, p],
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p],

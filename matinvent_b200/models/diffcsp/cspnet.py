@@ -25,8 +25,8 @@ from .graph import CrystalGraph
 MAX_ATOMIC_NUM = 100
 
 
-def _pad4(n):
-    return (n + 3) // 4 * 4
+def _pad8(n):
+    return (n + 7) // 8 * 8      # 32-byte blocks: the fp16 split copies stay 16-byte aligned for TMA
 
 
 class _Workspace:
@@ -113,13 +113,13 @@ class CSPNet(nn.Module):
         for name, shape in spec:
             n = math.prod(shape)
             self._slices[name] = (off, n, shape)
-            off += _pad4(n)
+            off += _pad8(n)
         self.flat = nn.Parameter(torch.zeros(off, device=dev, dtype=torch.float32))
         self._views, self._gviews = {}, {}
         self._flat_grad = None
         self._ws = {}
         self._graphs = {}
-        # tensor-core path (mi_tc_gemm): TF32 head / tail of every weight, refreshed when the weights change
+        # tensor-core path (mi_tc_gemm): fp16 head / scaled tail of every weight, refreshed when the weights change
         self.use_tc = True
         self._flat_hi = self._flat_lo = None
         self._hi, self._lo = {}, {}
@@ -145,7 +145,7 @@ class CSPNet(nn.Module):
         return r
 
     def weights_changed(self):
-        """Call after the flat weight buffer was written outside torch (mi_adam_step): the TF32 split copies
+        """Call after the flat weight buffer was written outside torch (mi_adam_step): the fp16 split copies
         used by the tensor-core GEMMs are rebuilt on the next forward."""
         self._tc_version = None
         if self.use_tc and self._flat_hi is not None:
@@ -156,14 +156,15 @@ class CSPNet(nn.Module):
         if self._tc_version == ver and self._flat_hi is not None:
             return
         if self._flat_hi is None:
-            self._flat_hi, self._flat_lo = torch.empty_like(self.flat.data), torch.empty_like(self.flat.data)
+            self._flat_hi = torch.empty_like(self.flat.data, dtype=torch.float16)
+            self._flat_lo = torch.empty_like(self.flat.data, dtype=torch.float16)
             self._hi = {k: self._flat_hi[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
             self._lo = {k: self._flat_lo[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
-        ops.tf32_split(self.flat.data, self._flat_hi, self._flat_lo)
+        ops.f16_split(self.flat.data, self._flat_hi, self._flat_lo)
         self._tc_version = ver
 
     def _linear(self, A, wname, C, M, **epi):
-        """C = epilogue(A @ W^T): tensor cores (3xTF32) when the operands are TMA-compatible, else FP32 FFMA."""
+        """C = epilogue(A @ W^T): tensor cores (split FP16) when the operands are TMA-compatible, else FP32 FFMA."""
         W = self._views[wname]
         if self.use_tc and ops.tc_ok(A, W):
             return ops.tc_gemm(A, self._hi[wname], self._lo[wname], C, M=M, **epi)

@@ -92,20 +92,23 @@ def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk):
     return e
 
 
-def tf32_split(w, hi, lo):
-    _f32(w), _f32(hi), _f32(lo)
-    check(lib().mi_tf32_split(_p(w), _p(hi), _p(lo), w.numel(), _stream()), "mi_tf32_split")
+def f16_split(w, hi, lo):
+    """hi = fp16(w), lo = fp16((w - hi) * 2^11): operands of the split-precision tensor-core GEMM."""
+    _f32(w)
+    if hi.dtype != torch.float16 or lo.dtype != torch.float16:
+        raise TypeError("hi/lo must be float16")
+    check(lib().mi_f16_split(_p(w), _p(hi), _p(lo), w.numel(), _stream()), "mi_f16_split")
 
 
 def tc_ok(A, W):
-    """operands usable by the TMA / tcgen05 path: 16-byte aligned rows"""
-    return (_ld(A) % 4 == 0 and _ld(W) % 4 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 16 == 0)
+    """operands usable by the TMA / tcgen05 path: 16-byte aligned rows (fp32 A: ld % 4, fp16 W copies: ld % 8)"""
+    return (_ld(A) % 4 == 0 and _ld(W) % 8 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 32 == 0)
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
             act=ACT_NONE, alpha=1.0, beta=0.0):
-    """C = epilogue(alpha * A @ W^T) on the tensor cores (3xTF32); W_hi/W_lo from tf32_split.  See mi_tc_gemm."""
-    for t in (A, W_hi, W_lo, C_, bias, z_out, z_in, resid):
+    """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm."""
+    for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K

@@ -12,8 +12,8 @@ shapes = [("edge1", 34445, 512, 768), ("edge2", 34445, 512, 512), ("pq", 2643, 1
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for name, M, N, K in shapes:
     A, W = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
-    hi, lo = torch.empty_like(W), torch.empty_like(W)
-    ops.tf32_split(W, hi, lo)
+    hi, lo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=torch.float16)
+    ops.f16_split(W, hi, lo)
     C = torch.empty(M, N, device="cuda")
     for kind in ("ffma", "tc"):
         ts = []

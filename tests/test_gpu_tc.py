@@ -17,24 +17,35 @@ def _rand(*s, seed=0):
 
 
 def _split(ops, W):
-    hi, lo = torch.empty_like(W), torch.empty_like(W)
-    ops.tf32_split(W, hi, lo)
+    hi, lo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=torch.float16)
+    ops.f16_split(W, hi, lo)
     return hi, lo
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 64), (128, 256, 768), (1, 8, 32), (300, 512, 512), (2643, 1024, 512),
-                                   (257, 100, 512), (130, 3, 512), (34445, 512, 768), (256, 512, 256), (77, 512, 100), (1000, 512, 1024)])
+                                   (257, 100, 512), (130, 3, 512), (34445, 512, 768), (256, 512, 256), (77, 512, 104), (1000, 512, 1024), (70000, 256, 64)])
 def test_tc_gemm_fp32_grade(M, N, K):
     from matinvent_b200 import ops
     A, W = _rand(M, K, seed=1), _rand(N, K, seed=2)
     hi, lo = _split(ops, W)
-    assert float((hi + lo - W).abs().max()) <= 2.0 ** -21 * float(W.abs().max())
+    assert float((hi.float() + lo.float() / 2048 - W).abs().max()) <= 2.0 ** -22 * float(W.abs().max())
     C = torch.full((M, N), float("nan"), device="cuda")
     ops.tc_gemm(A, hi, lo, C)
     ref = A.double() @ W.double().t()
     err = rel_err(C, ref)
     print("tc_gemm M=%d N=%d K=%d rel err %.2e" % (M, N, K, err))
     assert err < 5e-6, err
+
+
+def test_tc_gemm_rejects_unaligned_weights():
+    """K = 100 -> 200-byte fp16 rows: not TMA-legal; the host mirror routes such GEMMs to mi_sgemm (ops.tc_ok)."""
+    from matinvent_b200 import ops
+    from matinvent_b200._lib import MatInventLibError
+    A, W = _rand(8, 100, seed=1), _rand(16, 100, seed=2)
+    assert not ops.tc_ok(A, W)
+    hi, lo = _split(ops, W)
+    with pytest.raises(MatInventLibError):
+        ops.tc_gemm(A, hi, lo, torch.empty(8, 16, device="cuda"))
 
 
 def test_tc_gemm_fused_epilogue_and_views():
