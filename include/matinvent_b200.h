@@ -60,6 +60,10 @@ typedef struct {
     float alpha;
     float beta;
     int splitk;
+    float* amax_out;      /* optional [M]: row-wise max |C[m][:]| (atomic max; caller zeroes it first) */
+    const float* a_amax;  /* optional [M], mi_tc_gemm only: row-wise max |A[m][:]| from the producer of A; rows
+                             are rescaled by a power of two into fp16 range before the split (exact) and the
+                             result rows scaled back, so the tensor-core path keeps fp32 dynamic range */
 } mi_epilogue_t;
 
 int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
@@ -70,7 +74,7 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
  * MMAs per k-slice, TMA-staged swizzled operand tiles, two TMEM accumulators), same epilogue contract as
  * mi_sgemm (no split-K).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
  * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo,
- * and |values| < 65504. */
+ * and |W| < 65504; A rows larger than 2^15 need epi->a_amax (see mi_epilogue_t). */
 int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_stream_t stream);
 int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
                float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
@@ -98,9 +102,10 @@ int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, co
  * out[s][:] = scale_s * sum_{k in [ptr[s], ptr[s+1])} X[perm ? perm[k] : k][:]
  *   mean != 0: scale_s = 1 / max(count, 1) (torch_scatter.scatter(reduce='mean'), cspnet.py:79,281)
  *   mean == 0: plain sum.  accumulate != 0: out += result.
- * H must be a multiple of 4 and rows 16-byte aligned.  This is the edge-scatter roofline kernel. */
+ * H must be a multiple of 4 and rows 16-byte aligned.  amax_out (nullable, [S]) receives max |out[s][:]|
+ * (for the row rescaling of mi_tc_gemm).  This is the edge-scatter roofline kernel. */
 int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
-                      int S, int H, int mean, int accumulate, mi_stream_t stream);
+                      int S, int H, int mean, int accumulate, float* amax_out, mi_stream_t stream);
 
 /* dX[e][:] = dOut[idx[e]][:] * (inv_count ? 1/max(cnt(idx[e]),1) : 1) * (z ? silu'(z[e][:]) : 1)
  * (backward of segment mean + SiLU).  idx nullable -> identity; ptr = CSR used for counts (nullable ->

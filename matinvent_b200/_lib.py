@@ -19,7 +19,8 @@ class Epilogue(C.Structure):
                 ("z_out", c_fp), ("z_ld", C.c_int),
                 ("z_in", c_fp), ("zin_ld", C.c_int),
                 ("resid", c_fp), ("resid_ld", C.c_int),
-                ("act", C.c_int), ("alpha", C.c_float), ("beta", C.c_float), ("splitk", C.c_int)]
+                ("act", C.c_int), ("alpha", C.c_float), ("beta", C.c_float), ("splitk", C.c_int),
+                ("amax_out", c_fp), ("a_amax", c_fp)]
 
 
 i, f, d, ll, u64, p = C.c_int, C.c_float, C.c_double, C.c_longlong, C.c_ulonglong, c_fp
@@ -33,7 +34,7 @@ PROTOTYPES = {
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p],
-    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p],
+    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p],
     "mi_colsum": [p, i, i, i, p, i, p],
     "mi_layernorm_fwd": [p, i, p, p, p, i, p, p, i, i, f, p],

@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(NT, 2) sgemm_kernel(const GemmParams p) {
                     v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                 }
                 *reinterpret_cast<float4*>(crow) = make_float4(v[0], v[1], v[2], v[3]);
+                if (e.amax_out)
+                    atomicMax(reinterpret_cast<unsigned*>(e.amax_out + m),
+                              __float_as_uint(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])))));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(NT, 2) sgemm_kernel(const GemmParams p) {
                     else if (e.act == MI_ACT_DSILU) x *= mi_dsilu(__ldg(e.z_in + (long long)m * e.zin_ld + n + j));
                     if (e.resid) x += __ldg(e.resid + (long long)m * e.resid_ld + n + j);
                     crow[j] = x;
+                    if (e.amax_out) atomicMax(reinterpret_cast<unsigned*>(e.amax_out + m), __float_as_uint(fabsf(x)));
                 }
             }
         }
@@ -237,6 +241,7 @@ extern "C" int mi_sgemm(int transA, int transB, int M, int N, int K, const float
     }
     if (p.e.splitk < 1) p.e.splitk = 1;
     if (p.e.splitk > 1) {
+        MI_CHECK_ARG(!p.e.amax_out, "split-K cannot report row maxima");
         MI_CHECK_ARG(!p.e.bias && !p.e.g1 && !p.e.g2 && !p.e.g3 && !p.e.z_out && !p.e.resid &&
                      p.e.act == MI_ACT_NONE && p.e.beta == 1.f, "split-K needs a plain accumulate epilogue");
     }

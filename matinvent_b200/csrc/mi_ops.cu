@@ -101,60 +101,57 @@ __global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __rest
                                                              const int* __restrict__ ptr,
                                                              const int* __restrict__ perm,
                                                              float* __restrict__ out, int ldo, int H4,
-                                                             int mean, int accumulate) {
+                                                             int mean, int accumulate, float* __restrict__ amax_out) {
     const int s = blockIdx.x;
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c >= H4) return;
-    const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    int k = beg;
-    if (perm) {
-        for (; k + 4 <= end; k += 4) {
-            int r0 = __ldg(perm + k), r1 = __ldg(perm + k + 1), r2 = __ldg(perm + k + 2), r3 = __ldg(perm + k + 3);
-            float4 v0 = __ldcs(reinterpret_cast<const float4*>(X + (long long)r0 * ldx) + c);
-            float4 v1 = __ldcs(reinterpret_cast<const float4*>(X + (long long)r1 * ldx) + c);
-            float4 v2 = __ldcs(reinterpret_cast<const float4*>(X + (long long)r2 * ldx) + c);
-            float4 v3 = __ldcs(reinterpret_cast<const float4*>(X + (long long)r3 * ldx) + c);
-            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-            a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-        }
-        for (; k < end; ++k) {
-            int r0 = __ldg(perm + k);
-            float4 v0 = __ldcs(reinterpret_cast<const float4*>(X + (long long)r0 * ldx) + c);
-            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        }
-    } else {
-        const float4* base = reinterpret_cast<const float4*>(X) + c;
+    const bool live = c < H4;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
+        float4 a0 = r, a1 = r, a2 = r, a3 = r;
         const long long ld4 = ldx >> 2;
+        const float4* base = reinterpret_cast<const float4*>(X) + c;
+        int k = beg;
         for (; k + 4 <= end; k += 4) {
-            float4 v0 = __ldcs(base + (long long)k * ld4);
-            float4 v1 = __ldcs(base + (long long)(k + 1) * ld4);
-            float4 v2 = __ldcs(base + (long long)(k + 2) * ld4);
-            float4 v3 = __ldcs(base + (long long)(k + 3) * ld4);
+            long long r0 = perm ? __ldg(perm + k) : k, r1 = perm ? __ldg(perm + k + 1) : k + 1;
+            long long r2 = perm ? __ldg(perm + k + 2) : k + 2, r3 = perm ? __ldg(perm + k + 3) : k + 3;
+            float4 v0 = __ldcs(base + r0 * ld4), v1 = __ldcs(base + r1 * ld4);
+            float4 v2 = __ldcs(base + r2 * ld4), v3 = __ldcs(base + r3 * ld4);
             a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
             a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
             a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
             a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
         }
         for (; k < end; ++k) {
-            float4 v0 = __ldcs(base + (long long)k * ld4);
+            long long r0 = perm ? __ldg(perm + k) : k;
+            float4 v0 = __ldcs(base + r0 * ld4);
             a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         }
+        r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                        (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+        if (mean) {
+            float cnt = (float)max(end - beg, 1);
+            r.x /= cnt; r.y /= cnt; r.z /= cnt; r.w /= cnt;
+        }
+        float4* o = reinterpret_cast<float4*>(out + (long long)s * ldo) + c;
+        if (accumulate) {
+            float4 t = *o;
+            r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+        }
+        *o = r;
     }
-    float4 r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
-                           (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
-    if (mean) {
-        float cnt = (float)max(end - beg, 1);
-        r.x /= cnt; r.y /= cnt; r.z /= cnt; r.w /= cnt;
+    if (amax_out) {          // block-wide max |out[s][:]| (row rescaling of the tensor-core GEMM that consumes it)
+        __shared__ float wm[4];
+        float mx = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mx = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
+            atomicMax(reinterpret_cast<unsigned*>(amax_out + s), __float_as_uint(mx));
+        }
     }
-    float4* o = reinterpret_cast<float4*>(out + (long long)s * ldo) + c;
-    if (accumulate) {
-        float4 t = *o;
-        r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
-    }
-    *o = r;
 }
 
 __global__ void gather_rows_dsilu_kernel(const float* __restrict__ dOut, int ldd, const int* __restrict__ idx,
@@ -628,13 +625,13 @@ extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* e
 }
 
 extern "C" int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
-                                 int S, int H, int mean, int accumulate, mi_stream_t stream) {
+                                 int S, int H, int mean, int accumulate, float* amax_out, mi_stream_t stream) {
     MI_CHECK_ARG(S >= 0 && H > 0 && H % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "H, ldx, ldo must be multiples of 4");
     if (S == 0) return MI_OK;
     MI_CHECK_ARG(X && ptr && out && mi_host_aligned16(X) && mi_host_aligned16(out), "null or unaligned pointer");
     int H4 = H / 4;
     dim3 grid(S, mi_div_up(H4, 128));
-    segment_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, ptr, perm, out, ldo, H4, mean, accumulate);
+    segment_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, ptr, perm, out, ldo, H4, mean, accumulate, amax_out);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

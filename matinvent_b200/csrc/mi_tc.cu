@@ -40,7 +40,7 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_RAW + 2 * A_H + 2 * W_H;
     static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
     static constexpr int EBUF_BYTES = 8 * 32 * EPITCH * 4;        // per-warp transpose buffers of the epilogue
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 256 /*barriers*/;   // 231 680 B at TN = 256
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 128 /*barriers*/ + 256 /*row exponents*/;   // 231 808 B at TN = 256
     static constexpr uint32_t TMEM_COLS = 2 * TN;                 // main + correction accumulators
     // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
@@ -141,6 +141,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* acc_full = bars + 3 * STAGES;        // accumulators of the current tile complete
     uint64_t* acc_empty = bars + 3 * STAGES + 1;   // epilogue has drained TMEM
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+    int8_t* rexp_all = reinterpret_cast<int8_t*>(smem + STAGES * STAGE_BYTES + C::EBUF_BYTES + 128);   // [2][128] power-of-two row exponents
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + TK - 1) / TK;
@@ -229,7 +230,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
+            int8_t* rexp = rexp_all + (tcount & 1) * 128;
             if (warp < 6) {
+                // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
+                // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
+                // the split — exact — and the result row by the inverse in the epilogue.
+                {
+                    int e8 = 0;
+                    const int m = m0 + t;
+                    if (e.a_amax && m < p.M) {
+                        const int ex = (int)((__float_as_uint(__ldg(e.a_amax + m)) >> 23) & 0xff) - 127;
+                        e8 = max(-100, min(ex - 14, 100));
+                    }
+                    rexp[t] = (int8_t)e8;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -242,7 +257,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int pidx = i * 128 + t;                     // physical float4 slot in the 128B-swizzled fp32 tile
                         const int row = pidx >> 3;
                         const int k0 = ((pidx & 7) ^ (row & 7)) << 2;     // logical k of the slot (Swizzle<3,4,3>)
-                        const float4 v = raw[pidx];
+                        float4 v = raw[pidx];
+                        const float sc = __uint_as_float((uint32_t)(127 - (int)rexp[row]) << 23);      // 2^-e, exact
+                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
                         uint2 h, l;
                         split2(v.x, v.y, h.x, l.x);
                         split2(v.z, v.w, h.y, l.y);
@@ -298,10 +315,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 if (nb >= p.N) continue;                 // warp-uniform
 #pragma unroll
+                const float rowsc = e.alpha * __uint_as_float((uint32_t)(127 + (int)rexp[q * 32 + lane]) << 23);   // alpha * 2^e
+#pragma unroll
                 for (int j = 0; j < 32; j += 2)          // STS.64, bank = (2*lane + j) % 32: conflict-free
                     *reinterpret_cast<float2*>(ebuf + lane * EP + j) = make_float2(
-                        e.alpha * fmaf(__uint_as_float(w[j]), LO_UNSCALE, __uint_as_float(v[j])),
-                        e.alpha * fmaf(__uint_as_float(w[j + 1]), LO_UNSCALE, __uint_as_float(v[j + 1])));
+                        rowsc * fmaf(__uint_as_float(w[j]), LO_UNSCALE, __uint_as_float(v[j])),
+                        rowsc * fmaf(__uint_as_float(w[j + 1]), LO_UNSCALE, __uint_as_float(v[j + 1])));
                 __syncwarp();
                 const int col4 = (lane & 7) * 4;
                 const int n = nb + col4;
@@ -318,7 +337,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         r2 = __shfl_sync(0xffffffffu, i2, rr);
                         r3 = __shfl_sync(0xffffffffu, i3, rr);
                     }
-                    if (m >= p.M || n >= p.N) continue;
+                    const bool active = (m < p.M) && (n < p.N);
+                    float rmax = 0.f;
+                    if (active) {
                     const float2 xa = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4);
                     const float2 xb = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4 + 2);
                     float x[4] = {xa.x, xa.y, xb.x, xb.y};
@@ -337,6 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                         if (e.resid) { float4 tq = __ldg(reinterpret_cast<const float4*>(e.resid + (long long)m * e.resid_ld + n)); x[0] += tq.x; x[1] += tq.y; x[2] += tq.z; x[3] += tq.w; }
                         *reinterpret_cast<float4*>(crow) = make_float4(x[0], x[1], x[2], x[3]);
+                        rmax = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
                     } else {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -352,7 +374,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             if (e.act == MI_ACT_SILU) y = silu_fast(y);
                             if (e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
                             crow[u] = y;
+                            rmax = fmaxf(rmax, fabsf(y));
                         }
+                    }
+                    }
+                    if (e.amax_out) {                                  // row max over the 8 lanes that share row rr
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 4));
+                        if (active && (lane & 7) == 0) atomicMax(reinterpret_cast<unsigned*>(e.amax_out + m), __float_as_uint(rmax));
                     }
                 }
                 __syncwarp();

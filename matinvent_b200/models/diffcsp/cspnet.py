@@ -59,6 +59,16 @@ class _Workspace:
         self.pred_l = buf(B, 3, 3)
         self.pred_x = buf(N, 3)
         self.pred_a = buf(N, A)
+        # row-wise max |.| of the activations that feed tensor-core GEMMs (power-of-two row rescaling keeps the
+        # fp16 split path inside fp32 dynamic range); zeroed at the start of every forward
+        self.amax = torch.zeros(N + L * (E + 2 * N), device=dev, dtype=f32)
+        self.amax_h0 = self.amax[:N]
+        o = N
+        self.amax_a1, self.amax_agg, self.amax_an1 = [], [], []
+        for _ in range(L):
+            self.amax_a1.append(self.amax[o:o + E]); o += E
+            self.amax_agg.append(self.amax[o:o + N]); o += N
+            self.amax_an1.append(self.amax[o:o + N]); o += N
         if train:
             self.z1 = [buf(E, H) for _ in range(L)]
             self.z2 = [buf(E, H) for _ in range(L)]
@@ -336,9 +346,10 @@ class CSPNet(nn.Module):
         if self.use_tc:
             self._refresh_tc()
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
-        self._linear(a, "emb_w", ws.h0, N, bias=W["emb_b"])
+        ws.amax.zero_()
+        self._linear(a, "emb_w", ws.h0, N, bias=W["emb_b"], amax_out=ws.amax_h0)
         self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
-        self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)])
+        self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
         ops.lattice_ip(l, ws.ips, B)
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi)
         for i in range(L):
@@ -357,14 +368,16 @@ class CSPNet(nn.Module):
             self._linear(ws.ips, q + "w_l", ws.cb, B, bias=W[q + "b1"])
             self._linear(ws.phi, q + "w_f", a1, E,
                          gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
-                         z_out=ws.z1[i] if train else None, act=ACT_SILU)
-            self._linear(a1, q + "w2", ws.a2, E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU)
+                         z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
+            self._linear(a1, q + "w2", ws.a2, E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU,
+                         a_amax=ws.amax_a1[i])
             # scatter-mean over the source node (cspnet.py:79)
-            ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True)
+            ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True, amax_out=ws.amax_agg[i])
             # node model + residual (cspnet.py:77-91)
-            self._linear(cat, q + "wn1", an1, N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU)
+            self._linear(cat, q + "wn1", an1, N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU,
+                         a_amax=ws.amax_agg[i], amax_out=ws.amax_an1[i])
             self._linear(an1, q + "wn2", h_out, N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
-                         act=ACT_SILU, resid=h_in)
+                         act=ACT_SILU, resid=h_in, a_amax=ws.amax_an1[i])
         hL = ws.h[L]
         if self.ln:
             ops.layernorm_fwd(hL, W["fin_g"], W["fin_b"], ws.hf, N, H,

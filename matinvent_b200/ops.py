@@ -46,9 +46,9 @@ def _ld(t):
 
 
 def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None, gathers=(), z_out=None,
-          z_in=None, resid=None, act=ACT_NONE, alpha=1.0, beta=0.0, splitk=1):
+          z_in=None, resid=None, act=ACT_NONE, alpha=1.0, beta=0.0, splitk=1, amax_out=None, a_amax=None):
     """C = epilogue(alpha * op(A) @ op(B)); see mi_sgemm.  A, B, C are 2-D row-major views.
-    gathers: up to three (tensor, index-or-None) pairs added row-wise."""
+    gathers: up to three (tensor, index-or-None) pairs added row-wise.  a_amax is ignored (fp32 has the range)."""
     for t in (A, B, C_, bias, z_out, z_in, resid):
         _f32(t)
     if M is None:
@@ -57,26 +57,16 @@ def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None
         K = A.shape[0] if transA else A.shape[1]
     if N is None:
         N = B.shape[0] if transB else B.shape[1]
-    e = Epilogue()
-    e.bias = _p(bias)
-    g = list(gathers) + [(None, None)] * (3 - len(gathers))
-    for k, (src, idx) in enumerate(g[:3]):
-        _f32(src)
-        _i32(idx)
-        setattr(e, "g%d" % (k + 1), _p(src))
-        setattr(e, "g%d_idx" % (k + 1), _p(idx))
-        setattr(e, "g%d_ld" % (k + 1), _ld(src) if src is not None else 0)
-    e.z_out, e.z_ld = _p(z_out), (_ld(z_out) if z_out is not None else 0)
-    e.z_in, e.zin_ld = _p(z_in), (_ld(z_in) if z_in is not None else 0)
-    e.resid, e.resid_ld = _p(resid), (_ld(resid) if resid is not None else 0)
-    e.act, e.alpha, e.beta, e.splitk = act, alpha, beta, splitk
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out, None)
     check(lib().mi_sgemm(int(transA), int(transB), M, N, K, A.data_ptr(), _ld(A), B.data_ptr(), _ld(B),
                          C_.data_ptr(), _ld(C_), C.byref(e), _stream()), "mi_sgemm")
     return C_
 
 
-def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk):
+def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out=None, a_amax=None):
     e = Epilogue()
+    _f32(amax_out), _f32(a_amax)
+    e.amax_out, e.a_amax = _p(amax_out), _p(a_amax)
     e.bias = _p(bias)
     g = list(gathers) + [(None, None)] * (3 - len(gathers))
     for k, (src, idx) in enumerate(g[:3]):
@@ -106,14 +96,14 @@ def tc_ok(A, W):
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
-            act=ACT_NONE, alpha=1.0, beta=0.0):
+            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None):
     """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm."""
     for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1)
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1, amax_out, a_amax)
     check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
                            _ld(C_), C.byref(e), _stream()), "mi_tc_gemm")
     return C_
@@ -132,10 +122,10 @@ def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi):
                                 _ld(phi), _stream()), "mi_edge_fourier")
 
 
-def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False):
-    _f32(X), _f32(out), _i32(ptr), _i32(perm)
+def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None):
+    _f32(X), _f32(out), _i32(ptr), _i32(perm), _f32(amax_out)
     check(lib().mi_segment_reduce(_p(X), _ld(X), _p(ptr), _p(perm), _p(out), _ld(out), S, H, int(mean),
-                                  int(accumulate), _stream()), "mi_segment_reduce")
+                                  int(accumulate), _p(amax_out), _stream()), "mi_segment_reduce")
     return out
 
 

@@ -128,6 +128,9 @@ def test_segment_reduce_and_gather_backward(ops):
     ops.segment_reduce(X, g.dst_ptr, out, g.N, H, perm=g.dst_perm, mean=False)
     ref = torch.zeros(g.N, H, dtype=torch.float64, device="cuda").index_add_(0, g.edge_dst.long(), X.double())
     assert rel_err(out, ref) < 1e-6
+    am = torch.zeros(g.N, device="cuda")
+    ops.segment_reduce(X, g.seg_ptr, out, g.N, H, mean=True, amax_out=am)
+    assert torch.equal(am, out.abs().amax(dim=1))
     # strided output + accumulate
     cat = torch.ones(g.N, 2 * H, device="cuda")
     ops.segment_reduce(X, g.seg_ptr, cat[:, H:], g.N, H, mean=False, accumulate=True)
