@@ -117,9 +117,9 @@ int mi_gather_rows_dsilu(const float* dOut, int ldd, const int* idx, const int* 
 int mi_colsum(const float* X, int ldx, int M, int N, float* out, int accumulate, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- LayerNorm (cspnet.py:57,86-88,142,277)
- */
+ * amax_out (nullable, [rows]): atomic max of |y[row][:]| (row rescaling of the tensor-core GEMM reading y) */
 int mi_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
-                     float* mean, float* rstd, int rows, int H, float eps, mi_stream_t stream);
+                     float* mean, float* rstd, int rows, int H, float eps, float* amax_out, mi_stream_t stream);
 /* dx (+)= LN backward; dgamma/dbeta += (atomics) */
 int mi_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma,
                      const float* mean, const float* rstd, float* dx, int lddx, int accumulate_dx,

@@ -198,7 +198,7 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                      float* __restrict__ mean_o, float* __restrict__ rstd_o, int rows, int H,
-                                     float eps) {
+                                     float eps, float* __restrict__ amax_out) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -212,7 +212,17 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx, const
     v = mi_warp_sum(v);
     float rstd = 1.0f / sqrtf(v / (float)H + eps);
     float* yr = y + (long long)row * ldy;
-    for (int c = lane; c < H; c += 32) yr[c] = (xr[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    float mx = 0.f;
+    for (int c = lane; c < H; c += 32) {
+        float yv = (xr[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        yr[c] = yv;
+        mx = fmaxf(mx, fabsf(yv));
+    }
+    if (amax_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned*>(amax_out + row), __float_as_uint(mx));
+    }
     if (lane == 0) {
         if (mean_o) mean_o[row] = mean;
         if (rstd_o) rstd_o[row] = rstd;
@@ -661,11 +671,11 @@ extern "C" int mi_colsum(const float* X, int ldx, int M, int N, float* out, int 
 }
 
 extern "C" int mi_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
-                                float* mean, float* rstd, int rows, int H, float eps, mi_stream_t stream) {
+                                float* mean, float* rstd, int rows, int H, float eps, float* amax_out, mi_stream_t stream) {
     MI_CHECK_ARG(rows >= 0 && H > 0, "bad sizes");
     if (rows == 0) return MI_OK;
     MI_CHECK_ARG(x && gamma && beta && y, "null pointer");
-    layernorm_fwd_kernel<<<mi_div_up(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, rows, H, eps);
+    layernorm_fwd_kernel<<<mi_div_up(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, rows, H, eps, amax_out);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

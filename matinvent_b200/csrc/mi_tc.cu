@@ -18,8 +18,9 @@
 //   * fused epilogue (bias + up to 3 row gathers + pre-activation store + SiLU + residual), same contract as
 //     mi_sgemm, 8 warps reading TMEM with tcgen05.ld.
 //
-// CTA = 128 x TN output tile (TN in {256,128,64}), 10 warps: w0 TMA producer, w1 MMA issuer + TMEM owner,
-// w2..5 split + epilogue, w6..9 epilogue.  Stage = A_raw 16K | A_hi 8K | A_lo 8K | W_hi TN*64 | W_lo TN*64.
+// Persistent CTA per SM, 128 x TN output tiles (TN in {128,64}), 14 warps: w0 TMA producer, w1 MMA issuer + TMEM
+// owner, w2..9 operand split, w10..17 epilogue (overlapped with the next tile's main loop: TMEM holds two
+// {main, correction} accumulator pairs).  Stage = A_raw 16K | A_hi 8K | A_lo 8K | W_hi TN*64 | W_lo TN*64, 4 stages.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -29,8 +30,8 @@
 
 namespace {
 
-constexpr int TM = 128;                              // CTA tile rows; columns TN in {256, 128, 64} (template)
-constexpr int TC_THREADS = 320;   // w0 TMA, w1 MMA, w2..5 split + epilogue, w6..9 epilogue only
+constexpr int TM = 128;                              // CTA tile rows; columns TN in {128, 64} (template)
+constexpr int TC_THREADS = 576;   // w0 TMA, w1 MMA, w2..9 operand split, w10..17 epilogue
 constexpr int TK = 32;                               // k-block: 32 elements = 128 B of fp32, 64 B of fp16
 template <int STAGES, int TN>
 struct Cfg {
@@ -40,8 +41,9 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_RAW + 2 * A_H + 2 * W_H;
     static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
     static constexpr int EBUF_BYTES = 8 * 32 * EPITCH * 4;        // per-warp transpose buffers of the epilogue
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 128 /*barriers*/ + 256 /*row exponents*/;   // 231 808 B at TN = 256
-    static constexpr uint32_t TMEM_COLS = 2 * TN;                 // main + correction accumulators
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 128 /*barriers*/ + 128 /*row exponents*/;
+    static constexpr uint32_t ACC_COLS = 2 * TN;                  // main + correction accumulators of one tile
+    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;           // double buffered: tile t+1 accumulates while t drains
     // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
     static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -138,10 +140,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t* full = bars;                 // [STAGES] TMA landed
     uint64_t* split = bars + STAGES;       // [STAGES] fp16 A tiles ready
     uint64_t* empty = bars + 2 * STAGES;   // [STAGES] MMAs done with the stage
-    uint64_t* acc_full = bars + 3 * STAGES;        // accumulators of the current tile complete
-    uint64_t* acc_empty = bars + 3 * STAGES + 1;   // epilogue has drained TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
-    int8_t* rexp_all = reinterpret_cast<int8_t*>(smem + STAGES * STAGE_BYTES + C::EBUF_BYTES + 128);   // [2][128] power-of-two row exponents
+    uint64_t* acc_full = bars + 3 * STAGES;        // [2] accumulators of a tile complete
+    uint64_t* acc_empty = bars + 3 * STAGES + 2;   // [2] epilogue has drained the accumulator buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    int8_t* rexp = reinterpret_cast<int8_t*>(smem + STAGES * STAGE_BYTES + C::EBUF_BYTES + 128);   // [128] row exponents (split warps only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + TK - 1) / TK;
@@ -152,11 +154,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], 128);
+            mbar_init(&split[s], 256);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 256);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 256);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -196,7 +200,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-                mbar_wait(acc_empty, (tcount & 1) ^ 1);          // previous tile's accumulators have been read out
+                const uint32_t ab = tcount & 1;                  // accumulator buffer of this tile
+                const uint32_t acc = tmem_base + ab * C::ACC_COLS;
+                mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);   // the tile two back has been read out of this buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -210,72 +216,91 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < TK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
-                        umma_f16(tmem_base, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                        umma_f16(tmem_base + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                        umma_f16(tmem_base + TN, d_ahi + adv, d_wlo + adv, IDESC, 1u);
+                        umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
+                        umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
+                        umma_f16(acc + TN, d_ahi + adv, d_wlo + adv, IDESC, 1u);
                     }
                     umma_commit(&empty[s]);
                 }
-                umma_commit(acc_full);
+                umma_commit(&acc_full[ab]);
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== operand split warps (w2..9) =====================
+        const int t = threadIdx.x - 64;     // 0..255
+        const mi_epilogue_t& e = p.e;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * TM;
+            // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
+            // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
+            // the split — exact — and the result row by the inverse in the epilogue.
+            {
+                int e8 = 0;
+                const int m = m0 + t;
+                if (e.a_amax && t < TM && m < p.M) {
+                    const int ex = (int)((__float_as_uint(__ldg(e.a_amax + m)) >> 23) & 0xff) - 127;
+                    e8 = max(-100, min(ex - 14, 100));
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done reading the previous tile's exponents
+                if (t < TM) rexp[t] = (int8_t)e8;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                const float4* raw = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
+                uint8_t* hi = smem + s * STAGE_BYTES + A_RAW;
+                uint8_t* lo = hi + A_H;
+                // all loads first (the stores below may alias them as far as the compiler knows), then convert + store
+                float4 v[4];
+                float sc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                         // 4 float4 per thread
+                    const int pidx = i * 256 + t;                     // physical float4 slot in the 128B-swizzled fp32 tile
+                    v[i] = raw[pidx];
+                    sc[i] = __uint_as_float((uint32_t)(127 - (int)rexp[pidx >> 3]) << 23);      // 2^-e, exact
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int pidx = i * 256 + t;
+                    const int row = pidx >> 3;
+                    const int k0 = ((pidx & 7) ^ (row & 7)) << 2;     // logical k of the slot (Swizzle<3,4,3>)
+                    uint2 h, l;
+                    split2(v[i].x * sc[i], v[i].y * sc[i], h.x, l.x);
+                    split2(v[i].z * sc[i], v[i].w * sc[i], h.y, l.y);
+                    // fp16 tile: 64-byte rows, 16-byte chunk index XOR (row/2)%4 (Swizzle<2,4,3>)
+                    const int off = row * 64 + ((((k0 >> 3) ^ (row >> 1)) & 3) << 4) + ((k0 & 7) << 1);
+                    *reinterpret_cast<uint2*>(hi + off) = h;
+                    *reinterpret_cast<uint2*>(lo + off) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+                mbar_arrive(&split[s]);
             }
         }
     } else {
-        // ===================== split warpgroup (w2..5) + epilogue (w2..9) =====================
-        const int t = threadIdx.x - 64;     // 0..127 for the split warps
+        // ===================== epilogue warps (w10..17), overlapped with the next tile's main loop =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int hf = (warp - 2) >> 2;              // column half handled by this warp
+        const int hf = (warp - 10) >> 2;             // column half handled by this warp
         constexpr int EP = C::EPITCH;
-        float* ebuf = ebuf_all + (warp - 2) * (32 * EP);
+        float* ebuf = ebuf_all + (warp - 10) * (32 * EP);
         const mi_epilogue_t& e = p.e;
-        uint32_t it = 0, tcount = 0;
+        uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
             const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
-            int8_t* rexp = rexp_all + (tcount & 1) * 128;
-            if (warp < 6) {
-                // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
-                // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
-                // the split — exact — and the result row by the inverse in the epilogue.
-                {
-                    int e8 = 0;
-                    const int m = m0 + t;
-                    if (e.a_amax && m < p.M) {
-                        const int ex = (int)((__float_as_uint(__ldg(e.a_amax + m)) >> 23) & 0xff) - 127;
-                        e8 = max(-100, min(ex - 14, 100));
-                    }
-                    rexp[t] = (int8_t)e8;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                }
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
-                    const float4* raw = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
-                    uint8_t* hi = smem + s * STAGE_BYTES + A_RAW;
-                    uint8_t* lo = hi + A_H;
-#pragma unroll
-                    for (int i = 0; i < (TM * TK / 4) / 128; ++i) {       // 8 float4 per thread
-                        const int pidx = i * 128 + t;                     // physical float4 slot in the 128B-swizzled fp32 tile
-                        const int row = pidx >> 3;
-                        const int k0 = ((pidx & 7) ^ (row & 7)) << 2;     // logical k of the slot (Swizzle<3,4,3>)
-                        float4 v = raw[pidx];
-                        const float sc = __uint_as_float((uint32_t)(127 - (int)rexp[row]) << 23);      // 2^-e, exact
-                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-                        uint2 h, l;
-                        split2(v.x, v.y, h.x, l.x);
-                        split2(v.z, v.w, h.y, l.y);
-                        // fp16 tile: 64-byte rows, 16-byte chunk index XOR (row/2)%4 (Swizzle<2,4,3>)
-                        const int off = row * 64 + ((((k0 >> 3) ^ (row >> 1)) & 3) << 4) + ((k0 & 7) << 1);
-                        *reinterpret_cast<uint2*>(hi + off) = h;
-                        *reinterpret_cast<uint2*>(lo + off) = l;
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-                    mbar_arrive(&split[s]);
-                }
-            }
+            const uint32_t ab = tcount & 1;
+            const uint32_t acc = tmem_base + ab * C::ACC_COLS;
             // ---- epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global traffic
-            mbar_wait(acc_full, tcount & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mrow = m0 + q * 32 + lane;                 // the row this lane owns in TMEM
+            int e8 = 0;                                          // same power-of-two row exponent as the split warps
+            if (e.a_amax && mrow < p.M) {
+                const int ex = (int)((__float_as_uint(__ldg(e.a_amax + mrow)) >> 23) & 0xff) - 127;
+                e8 = max(-100, min(ex - 14, 100));
+            }
+            const float rowsc = e.alpha * __uint_as_float((uint32_t)(127 + e8) << 23);   // alpha * 2^e
+            mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int i1 = 0, i2 = 0, i3 = 0;
             if (EPI & 1) {
                 const bool mrow_ok = mrow < p.M;
@@ -289,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int c = hf * CH + cc;
                 const int nb = n0 + c * 32;
                 uint32_t v[32], w[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+                const uint32_t taddr = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -311,11 +336,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (cc == CH - 1) {                      // all of this warp's TMEM reads are done: release the accumulators
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(acc_empty);
+                    mbar_arrive(&acc_empty[ab]);
                 }
                 if (nb >= p.N) continue;                 // warp-uniform
 #pragma unroll
-                const float rowsc = e.alpha * __uint_as_float((uint32_t)(127 + (int)rexp[q * 32 + lane]) << 23);   // alpha * 2^e
 #pragma unroll
                 for (int j = 0; j < 32; j += 2)          // STS.64, bank = (2*lane + j) % 32: conflict-free
                     *reinterpret_cast<float2*>(ebuf + lane * EP + j) = make_float2(
@@ -507,13 +531,11 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const vo
     if (e.z_in) cv = cv && (e.zin_ld % 4 == 0) && mi_host_aligned16(e.z_in);
     if (e.resid) cv = cv && (e.resid_ld % 4 == 0) && mi_host_aligned16(e.resid);
     p.c_vec = cv;
-    const long long mt = mi_div_up(M, TM);
-    int tn = 256;                                  // measured on B200: 128x128 tiles win below ~half a wave of 128x256 tiles
-    if (mt * mi_div_up(N, 256) < 74) tn = 128;
-    if (N <= 64) tn = 64;
-    else if (N <= 128) tn = 128;
+    // Column-tile width: 128 (two double-buffered {main, correction} accumulator pairs fill the 512 TMEM columns);
+    // 64 only for narrow outputs.
+    int tn = (N <= 64) ? 64 : 128;
     const char* force = getenv("MI_TC_TN");
-    if (force) tn = atoi(force);
+    if (force) tn = atoi(force) <= 64 ? 64 : 128;
     cudaStream_t s = (cudaStream_t)stream;
     const int epi_mode = ((p.e.g1 || p.e.g2 || p.e.g3) ? 1 : 0) | (p.e.z_out ? 2 : 0);
 #define MI_TC_CASE(ST, TNV)                                                                              \
@@ -523,7 +545,6 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const vo
         case 2: return launch_tc<ST, TNV, 2>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                    \
         default: return launch_tc<ST, TNV, 3>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                   \
     }
-    if (tn == 256) { MI_TC_CASE(3, 256) }
     if (tn == 128) { MI_TC_CASE(4, 128) }
     MI_TC_CASE(4, 64)
 #undef MI_TC_CASE

@@ -359,10 +359,13 @@ class CSPNet(nn.Module):
             h_in, h_out = ws.h[i], ws.h[i + 1]
             hn = cat[:, :H]
             if self.ln:
+                # the row maximum of cat = [LN(h) | agg] is accumulated by both producers (LayerNorm here, the scatter below)
                 ops.layernorm_fwd(h_in, W[q + "ln_g"], W[q + "ln_b"], hn, N, H,
-                                  ws.ln_mean[i] if train else None, ws.ln_rstd[i] if train else None)
+                                  ws.ln_mean[i] if train else None, ws.ln_rstd[i] if train else None,
+                                  amax_out=ws.amax_agg[i])
             else:
                 hn.copy_(h_in)
+                torch.maximum(ws.amax_agg[i], h_in.abs().amax(dim=1), out=ws.amax_agg[i])
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
             self._linear(hn, q + "w_pq", ws.pq, N)
             self._linear(ws.ips, q + "w_l", ws.cb, B, bias=W[q + "b1"])

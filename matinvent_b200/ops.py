@@ -142,11 +142,11 @@ def colsum(X, M, N, out, accumulate=True):
     return out
 
 
-def layernorm_fwd(x, gamma, beta, y, rows, H, mean=None, rstd=None, eps=1e-5):
-    for t in (x, gamma, beta, y, mean, rstd):
+def layernorm_fwd(x, gamma, beta, y, rows, H, mean=None, rstd=None, eps=1e-5, amax_out=None):
+    for t in (x, gamma, beta, y, mean, rstd, amax_out):
         _f32(t)
     check(lib().mi_layernorm_fwd(_p(x), _ld(x), _p(gamma), _p(beta), _p(y), _ld(y), _p(mean), _p(rstd), rows, H,
-                                 eps, _stream()), "mi_layernorm_fwd")
+                                 eps, _p(amax_out), _stream()), "mi_layernorm_fwd")
     return y
 
 
