@@ -128,6 +128,10 @@ int mi_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const f
 /* ---------------------------------------------------------------- small per-crystal pieces
  * ips[b] = vec(L_b L_b^T)  (cspnet.py:67-72) */
 int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stream);
+/* out[b][:] = bias + vec(L_b L_b^T) W^T with W [H,9]: the per-crystal term C_b of the split first edge linear
+ * (cspnet.py:45,67-72) in one launch */
+int mi_lattice_linear(const float* L, const float* W, const float* bias, float* out, int ldo, int B, int H,
+                      mi_stream_t stream);
 /* out[b] = A[b] (3x3) @ L[b] (3x3)   (cspnet.py:288-289); transL != 0 -> A[b] @ L[b]^T (its backward) */
 int mi_bmm3(const float* A, const float* L, float* out, int B, int transL, mi_stream_t stream);
 /* SinusoidalTimeEmbeddings (diffusion.py:53-66): out[b] = [sin(t_b f_k) || cos(t_b f_k)], dim even;

@@ -293,6 +293,25 @@ __global__ void lattice_ip_kernel(const float* __restrict__ L, float* __restrict
     const float* l = L + 9 * b;
     ips[t] = l[3 * r] * l[3 * c] + l[3 * r + 1] * l[3 * c + 1] + l[3 * r + 2] * l[3 * c + 2];
 }
+// out[b][n] = bias[n] + sum_k vec(L_b L_b^T)[k] * W[n][k]   (the lattice part of the first edge linear, cspnet.py:67-72)
+__global__ void lattice_linear_kernel(const float* __restrict__ L, const float* __restrict__ W, const float* __restrict__ bias,
+                                      float* __restrict__ out, int ldo, int H) {
+    __shared__ float ip[9];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 9) {
+        const float* l = L + 9 * b;
+        int r = threadIdx.x / 3, c = threadIdx.x % 3;
+        ip[threadIdx.x] = l[3 * r] * l[3 * c] + l[3 * r + 1] * l[3 * c + 1] + l[3 * r + 2] * l[3 * c + 2];
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < H; n += blockDim.x) {
+        const float* w = W + 9 * n;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc = fmaf(ip[k], __ldg(w + k), acc);
+        out[(long long)b * ldo + n] = acc + (bias ? __ldg(bias + n) : 0.f);
+    }
+}
 __global__ void bmm3_kernel(const float* __restrict__ A, const float* __restrict__ L, float* __restrict__ out,
                             int B, int transL) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -704,6 +723,14 @@ extern "C" int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stre
     if (B <= 0) return MI_OK;
     MI_CHECK_ARG(L && ips, "null pointer");
     lattice_ip_kernel<<<mi_div_up(9 * B, 256), 256, 0, (cudaStream_t)stream>>>(L, ips, B);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
+extern "C" int mi_lattice_linear(const float* L, const float* W, const float* bias, float* out, int ldo, int B, int H,
+                                 mi_stream_t stream) {
+    if (B <= 0) return MI_OK;
+    MI_CHECK_ARG(L && W && out && H > 0 && ldo >= H, "bad arguments");
+    lattice_linear_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(L, W, bias, out, ldo, H);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

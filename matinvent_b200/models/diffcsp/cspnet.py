@@ -176,7 +176,7 @@ class CSPNet(nn.Module):
     def _linear(self, A, wname, C, M, **epi):
         """C = epilogue(A @ W^T): tensor cores (split FP16) when the operands are TMA-compatible, else FP32 FFMA."""
         W = self._views[wname]
-        if self.use_tc and ops.tc_ok(A, W):
+        if self.use_tc and ops.tc_ok(A, self._hi[wname]):
             return ops.tc_gemm(A, self._hi[wname], self._lo[wname], C, M=M, **epi)
         return ops.sgemm(A, W, C, M=M, **epi)
 
@@ -347,7 +347,8 @@ class CSPNet(nn.Module):
             self._refresh_tc()
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
         ws.amax.zero_()
-        self._linear(a, "emb_w", ws.h0, N, bias=W["emb_b"], amax_out=ws.amax_h0)
+        # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
+        ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
         self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
         self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
         ops.lattice_ip(l, ws.ips, B)
@@ -368,7 +369,7 @@ class CSPNet(nn.Module):
                 torch.maximum(ws.amax_agg[i], h_in.abs().amax(dim=1), out=ws.amax_agg[i])
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
             self._linear(hn, q + "w_pq", ws.pq, N)
-            self._linear(ws.ips, q + "w_l", ws.cb, B, bias=W[q + "b1"])
+            ops.lattice_linear(l, W[q + "w_l"], W[q + "b1"], ws.cb, B, H)
             self._linear(ws.phi, q + "w_f", a1, E,
                          gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
                          z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])

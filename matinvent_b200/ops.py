@@ -92,7 +92,8 @@ def f16_split(w, hi, lo):
 
 def tc_ok(A, W):
     """operands usable by the TMA / tcgen05 path: 16-byte aligned rows (fp32 A: ld % 4, fp16 W copies: ld % 8)"""
-    return (_ld(A) % 4 == 0 and _ld(W) % 8 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % 32 == 0)
+    wa = 16 if W.dtype == torch.float16 else 32      # fp16 copy: its own alignment; fp32 master: the copy's is half
+    return (_ld(A) % 4 == 0 and _ld(W) % 8 == 0 and A.data_ptr() % 16 == 0 and W.data_ptr() % wa == 0)
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
@@ -162,6 +163,13 @@ def lattice_ip(L, ips, B):
     _f32(L), _f32(ips)
     check(lib().mi_lattice_ip(_p(L), _p(ips), B, _stream()), "mi_lattice_ip")
     return ips
+
+
+def lattice_linear(L, W, bias, out, B, H):
+    for t in (L, W, bias, out):
+        _f32(t)
+    check(lib().mi_lattice_linear(_p(L), _p(W), _p(bias), _p(out), _ld(out), B, H, _stream()), "mi_lattice_linear")
+    return out
 
 
 def bmm3(A, L, out, B, transL=False):

@@ -183,6 +183,10 @@ def test_small_per_crystal_ops(ops):
     ips = torch.empty(B, 9, device="cuda")
     ops.lattice_ip(L, ips, B)
     assert rel_err(ips, (L.double() @ L.double().transpose(1, 2)).view(B, 9)) < 1e-6
+    Wl, bl = _rand(512, 9, seed=33), _rand(512, seed=34)
+    cb = torch.empty(B, 512, device="cuda")
+    ops.lattice_linear(L, Wl, bl, cb, B, 512)
+    assert rel_err(cb, (L.double() @ L.double().transpose(1, 2)).view(B, 9) @ Wl.double().t() + bl.double()) < 1e-6
     A = _rand(B, 3, 3, seed=30)
     out = torch.empty(B, 3, 3, device="cuda")
     ops.bmm3(A, L, out, B)
