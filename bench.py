@@ -188,6 +188,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     from matinvent_b200 import _lib
