@@ -261,27 +261,32 @@ def main():
             q = "l%d." % i
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            dec._linear(ws.phi, q + "w_f", ws.a1[0], g.E,
-                        gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
-                        act=ops.ACT_SILU)
+            epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
+                        act=ops.ACT_SILU, amax_out=ws.amax_a1[i])
+            if dec.use_tc:
+                ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, dec._hi[q + "w_f"], dec._lo[q + "w_f"], ws.a1[0], M=g.E, **epi1)
+            else:
+                dec._linear(ws.phi, q + "w_f", ws.a1[0], g.E, **epi1)
             e1.record()
-            dec._linear(ws.a1[0], q + "w2", ws.a2, g.E, bias=W(q + "b2"), act=ops.ACT_SILU)
+            dec._linear(ws.a1[0], q + "w2", ws.a2, g.E, bias=W(q + "b2"), act=ops.ACT_SILU, a_amax=ws.amax_a1[i])
             e2.record()
             evs.append((e0, e1, e2))
     torch.cuda.synchronize()
     t_pair = statistics.mean(a.elapsed_time(c) for a, b, c in evs[HP["num_layers"]:]) / 1e3     # s per (GEMM1+GEMM2)
+    t_g1 = statistics.mean(a.elapsed_time(b) for a, b, c in evs[HP["num_layers"]:]) * 1e3      # us
+    t_g2 = statistics.mean(b.elapsed_time(c) for a, b, c in evs[HP["num_layers"]:]) * 1e3
     fl_pair = 2 * g.E * (F6 * H + H * H)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = fl_pair / t_pair / 1e12
-    kname = "tc_gemm_kernel (tcgen05 3xTF32)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)"
+    kname = "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)"
     roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM pair Phi.W_F^T + gathers + SiLU, then .W_2^T + SiLU",
                     achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None,
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    note="achieved = algorithmic FP32 FLOPs / time; FP32-grade accuracy costs 3 TF32 MMAs per product at half the "
-                         "bf16 rate, so the ceiling of this number is peak/6 (1e-4 parity over 2000 chained forwards rules out "
-                         "plain TF32/BF16); share of step = %.2f" % (2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
-                    mma_tflops=3 * ach, frac_of_tf32_peak=3 * ach / (peak_tf / 2))
+                    note="achieved = algorithmic FP32 FLOPs / time; FP32-grade accuracy costs 3 fp16 MMAs per product (x = hi + "
+                         "2^-11 lo), so the ceiling of this number is peak/3 (1e-4 parity over 2000 chained forwards rules out "
+                         "plain TF32/BF16/FP16 inputs); share of step = %.2f" % (2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
+                    mma_tflops=3 * ach, frac_mma_of_peak=3 * ach / peak_tf, us_gemm1=t_g1, us_gemm2=t_g2)
     # the edge-scatter (segment-mean) kernel against the HBM roofline, in isolation, L2 flushed between launches
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     seg = []

@@ -78,6 +78,11 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
 int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_stream_t stream);
 int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
                float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
+/* Same, with A already split by its producer into fp16 (hi, 2^11-scaled lo) arrays of leading dimension lda
+ * (lda % 8 == 0): the operand tiles are loaded by TMA directly, no in-kernel split (mi_edge_fourier emits this
+ * form of the Fourier basis, which is bounded by 1 and needs no row rescaling). */
+int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                        const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- graph construction
  * Fully-connected intra-crystal edges, row-major by (i, j) incl. i == j
@@ -94,9 +99,11 @@ int mi_fc_edges(const int* node_off, const int* edge_off, int B, int N, int E, i
  * -( -(x[dst] - x[src] + cell_off[e]) ) restated as x[dst]-x[src]+cell_off (knn, cspnet.py:252-257),
  * followed by the Fourier basis Phi[e] = [sin(d_c * 2 pi k)]_{c<3,k<F} || [cos(...)] (cspnet.py:12-24),
  * evaluated with the reference's fp32 arithmetic (arg = d * float(2 pi k)).
- * frac_diff (nullable) [E,3]; phi [E, 6F] with leading dimension ld_phi. */
+ * frac_diff (nullable) [E,3]; phi (nullable) [E, 6F] fp32 with leading dimension ld_phi; phi_hi / phi_lo
+ * (nullable pair) the same matrix as fp16 head + 2^11-scaled tail for mi_tc_gemm_presplit (same ld). */
 int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, const float* cell_off,
-                    int E, int F, float* frac_diff, float* phi, int ld_phi, mi_stream_t stream);
+                    int E, int F, float* frac_diff, float* phi, int ld_phi, void* phi_hi, void* phi_lo,
+                    mi_stream_t stream);
 
 /* ---------------------------------------------------------------- segment reductions
  * out[s][:] = scale_s * sum_{k in [ptr[s], ptr[s+1])} X[perm ? perm[k] : k][:]

@@ -32,8 +32,9 @@ PROTOTYPES = {
     "mi_sgemm": [i, i, i, i, i, p, i, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_f16_split": [p, p, p, ll, p],
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
+    "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
-    "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p],
+    "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, p],
     "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p],
     "mi_colsum": [p, i, i, i, p, i, p],

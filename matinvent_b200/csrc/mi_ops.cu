@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "mi_common.cuh"
 
 // ------------------------------------------------------------------------------------ error plumbing
@@ -74,7 +76,7 @@ __global__ void fc_edges_kernel(const int* __restrict__ node_off, const int* __r
 __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __restrict__ src,
                                     const int* __restrict__ dst, const float* __restrict__ cell_off,
                                     int E, int F, float* __restrict__ frac_diff, float* __restrict__ phi,
-                                    int ld_phi) {
+                                    int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int F3 = 3 * F;
     if (t >= (long long)E * F3) return;
@@ -90,66 +92,100 @@ __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __re
     float arg = __fmul_rn(d, freq);
     float s, co;
     sincosf(arg, &s, &co);
-    float* row = phi + (long long)e * ld_phi;
-    row[col] = s;
-    row[F3 + col] = co;
+    if (phi) {
+        float* row = phi + (long long)e * ld_phi;
+        row[col] = s;
+        row[F3 + col] = co;
+    }
+    if (phi_hi) {      // operand form of mi_tc_gemm_presplit: fp16 head + 2^11-scaled fp16 tail (|Phi| <= 1: no rescaling)
+        const long long o = (long long)e * ld_phi;
+        __half hs = __float2half_rn(s), hc = __float2half_rn(co);
+        phi_hi[o + col] = hs;
+        phi_hi[o + F3 + col] = hc;
+        phi_lo[o + col] = __float2half_rn((s - __half2float(hs)) * 2048.0f);
+        phi_lo[o + F3 + col] = __float2half_rn((co - __half2float(hc)) * 2048.0f);
+    }
 }
 
 // ------------------------------------------------------------------------------------ segment reduce
-// grid (S, ceil(H/4/128)); thread = one float4 column of one segment.
+// Persistent blocks (a multiple of the SM count) walk the segments grid-stride; thread = one float4 column of
+// one segment; 8 independent 128-bit streaming loads in flight per thread (rows of a segment are consecutive
+// 2 KB lines, so every warp request is fully coalesced).
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __restrict__ X, int ldx,
                                                              const int* __restrict__ ptr,
                                                              const int* __restrict__ perm,
-                                                             float* __restrict__ out, int ldo, int H4,
+                                                             float* __restrict__ out, int ldo, int H4, int S,
                                                              int mean, int accumulate, float* __restrict__ amax_out) {
-    const int s = blockIdx.x;
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     const bool live = c < H4;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-        const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
-        float4 a0 = r, a1 = r, a2 = r, a3 = r;
-        const long long ld4 = ldx >> 2;
-        const float4* base = reinterpret_cast<const float4*>(X) + c;
-        int k = beg;
-        for (; k + 4 <= end; k += 4) {
-            long long r0 = perm ? __ldg(perm + k) : k, r1 = perm ? __ldg(perm + k + 1) : k + 1;
-            long long r2 = perm ? __ldg(perm + k + 2) : k + 2, r3 = perm ? __ldg(perm + k + 3) : k + 3;
-            float4 v0 = __ldcs(base + r0 * ld4), v1 = __ldcs(base + r1 * ld4);
-            float4 v2 = __ldcs(base + r2 * ld4), v3 = __ldcs(base + r3 * ld4);
-            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-            a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-        }
-        for (; k < end; ++k) {
-            long long r0 = perm ? __ldg(perm + k) : k;
-            float4 v0 = __ldcs(base + r0 * ld4);
-            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        }
-        r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
-                        (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
-        if (mean) {
-            float cnt = (float)max(end - beg, 1);
-            r.x /= cnt; r.y /= cnt; r.z /= cnt; r.w /= cnt;
-        }
-        float4* o = reinterpret_cast<float4*>(out + (long long)s * ldo) + c;
-        if (accumulate) {
-            float4 t = *o;
-            r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
-        }
-        *o = r;
-    }
-    if (amax_out) {          // block-wide max |out[s][:]| (row rescaling of the tensor-core GEMM that consumes it)
-        __shared__ float wm[4];
-        float mx = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w)));
+    const long long ld4 = ldx >> 2;
+    const float4* base = reinterpret_cast<const float4*>(X) + c;
+    __shared__ float wm[4];
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const int beg = __ldg(ptr + s), end = __ldg(ptr + s + 1);
+            float4 a0 = r, a1 = r, a2 = r, a3 = r;
+            int k = beg;
+            for (; k + 8 <= end; k += 8) {
+                long long rr[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mx = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
-            atomicMax(reinterpret_cast<unsigned*>(amax_out + s), __float_as_uint(mx));
+                for (int u = 0; u < 8; ++u) rr[u] = perm ? (long long)__ldg(perm + k + u) : (long long)(k + u);
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_stream(base + rr[u] * ld4);
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
+                    a1.x += v[u + 1].x; a1.y += v[u + 1].y; a1.z += v[u + 1].z; a1.w += v[u + 1].w;
+                    a2.x += v[u + 2].x; a2.y += v[u + 2].y; a2.z += v[u + 2].z; a2.w += v[u + 2].w;
+                    a3.x += v[u + 3].x; a3.y += v[u + 3].y; a3.z += v[u + 3].z; a3.w += v[u + 3].w;
+                }
+            }
+            for (; k + 4 <= end; k += 4) {
+                long long r0 = perm ? __ldg(perm + k) : k, r1 = perm ? __ldg(perm + k + 1) : k + 1;
+                long long r2 = perm ? __ldg(perm + k + 2) : k + 2, r3 = perm ? __ldg(perm + k + 3) : k + 3;
+                float4 v0 = ld_stream(base + r0 * ld4), v1 = ld_stream(base + r1 * ld4);
+                float4 v2 = ld_stream(base + r2 * ld4), v3 = ld_stream(base + r3 * ld4);
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+                a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+                a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+                a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+            }
+            for (; k < end; ++k) {
+                long long r0 = perm ? __ldg(perm + k) : k;
+                float4 v0 = ld_stream(base + r0 * ld4);
+                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            }
+            r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                            (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+            if (mean) {
+                float cnt = (float)max(end - beg, 1);
+                r.x /= cnt; r.y /= cnt; r.z /= cnt; r.w /= cnt;
+            }
+            float4* o = reinterpret_cast<float4*>(out + (long long)s * ldo) + c;
+            if (accumulate) {
+                float4 t = *o;
+                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+            }
+            *o = r;
+        }
+        if (amax_out) {          // block-wide max |out[s][:]| (row rescaling of the tensor-core GEMM that consumes it)
+            float mx = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w)));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mx = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
+                atomicMax(reinterpret_cast<unsigned*>(amax_out + s), __float_as_uint(mx));
+            }
+            __syncthreads();
         }
     }
 }
@@ -642,13 +678,14 @@ extern "C" int mi_fc_edges(const int* node_off, const int* edge_off, int B, int 
 }
 
 extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, const float* cell_off,
-                               int E, int F, float* frac_diff, float* phi, int ld_phi, mi_stream_t stream) {
+                               int E, int F, float* frac_diff, float* phi, int ld_phi, void* phi_hi, void* phi_lo,
+                               mi_stream_t stream) {
     MI_CHECK_ARG(E >= 0 && F > 0 && ld_phi >= 6 * F, "bad sizes");
     if (E == 0) return MI_OK;
-    MI_CHECK_ARG(x && edge_src && edge_dst && phi, "null pointer");
+    MI_CHECK_ARG(x && edge_src && edge_dst && (phi || phi_hi) && ((phi_hi == nullptr) == (phi_lo == nullptr)), "null pointer");
     long long n = (long long)E * 3 * F;
     edge_fourier_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F,
-                                                                              frac_diff, phi, ld_phi);
+                                                                              frac_diff, phi, ld_phi, (__half*)phi_hi, (__half*)phi_lo);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -659,8 +696,18 @@ extern "C" int mi_segment_reduce(const float* X, int ldx, const int* ptr, const 
     if (S == 0) return MI_OK;
     MI_CHECK_ARG(X && ptr && out && mi_host_aligned16(X) && mi_host_aligned16(out), "null or unaligned pointer");
     int H4 = H / 4;
-    dim3 grid(S, mi_div_up(H4, 128));
-    segment_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, ptr, perm, out, ldo, H4, mean, accumulate, amax_out);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        MI_CUDA(cudaGetDevice(&dev));
+        MI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int gy = mi_div_up(H4, 128);
+    int gx = sms * 16 / gy;                       // 16 resident 128-thread blocks per SM: one full wave, grid-stride
+    if (gx > S) gx = S;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, gy);
+    segment_reduce_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ldx, ptr, perm, out, ldo, H4, S, mean, accumulate, amax_out);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

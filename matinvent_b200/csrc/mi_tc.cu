@@ -82,13 +82,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 // K-major fp16 operand tile, 64-byte rows, SWIZZLE_64B: 8-row groups of 512 B (SBO), LBO unused (=1),
 // descriptor version 1, layout type 4.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int sw128 = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)((sw128 ? 1024 : 512) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
+    d |= (uint64_t)(sw128 ? 2 : 4) << 61;
     return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -121,13 +121,15 @@ struct TcParams {
     float* C; int ldc;
     mi_epilogue_t e;
     int c_vec;
+    int presplit; // A is given as two fp16 arrays (hi, scaled lo): TMA loads them straight into the operand tiles
+    int dbg;      // MI_TC_DBG (profiling experiments only): 1 = no A loads, 2 = no operand split, 4 = no W loads, 8 = no MMA
 };
 
 // EPI bit 0: row gathers present, bit 1: pre-activation store (training).  bias / SiLU / residual stay runtime flags.
 template <int STAGES, int TN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
-               const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so the CTAs that share an A row
     // block run at the same time and hit it in L2).  Pipeline counters run across tiles, so the producer already
     // streams the next tile's first stages while this tile's epilogue drains TMEM.
@@ -165,6 +167,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAlo) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWlo) : "memory");
     }
@@ -188,10 +191,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], A_RAW + 2 * W_H);
-                    tma_load_2d(st, &mapA, &full[s], kb * TK, m0);
-                    tma_load_2d(st + A_RAW + 2 * A_H, &mapWhi, &full[s], kb * TK, n0);
-                    tma_load_2d(st + A_RAW + 2 * A_H + W_H, &mapWlo, &full[s], kb * TK, n0);
+                    mbar_expect_tx(&full[s], ((p.dbg & 1) ? 0 : (p.presplit ? 2 * A_H : A_RAW)) + ((p.dbg & 4) ? 0 : 2 * W_H));
+                    if (p.presplit) {
+                        tma_load_2d(st + A_RAW, &mapA, &full[s], kb * TK, m0);
+                        tma_load_2d(st + A_RAW + A_H, &mapAlo, &full[s], kb * TK, m0);
+                    } else if (!(p.dbg & 1)) tma_load_2d(st, &mapA, &full[s], kb * TK, m0);
+                    if (!(p.dbg & 4)) {
+                        tma_load_2d(st + A_RAW + 2 * A_H, &mapWhi, &full[s], kb * TK, n0);
+                        tma_load_2d(st + A_RAW + 2 * A_H + W_H, &mapWlo, &full[s], kb * TK, n0);
+                    }
                 }
             }
         }
@@ -208,13 +216,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
-                    mbar_wait(&split[s], ph);
+                    if (!p.presplit) mbar_wait(&split[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t d_ahi = umma_desc(st + A_RAW), d_alo = umma_desc(st + A_RAW + A_H);
-                    const uint64_t d_whi = umma_desc(st + A_RAW + 2 * A_H), d_wlo = umma_desc(st + A_RAW + 2 * A_H + W_H);
+                    const int sw = (p.dbg & 16) ? 1 : 0;      // timing experiment only (wrong results)
+                    const uint64_t d_ahi = umma_desc(st + A_RAW, sw), d_alo = umma_desc(st + A_RAW + A_H, sw);
+                    const uint64_t d_whi = umma_desc(st + A_RAW + 2 * A_H, sw), d_wlo = umma_desc(st + A_RAW + 2 * A_H + W_H, sw);
 #pragma unroll
-                    for (int k = 0; k < TK / 16; ++k) {
+                    for (int k = 0; k < ((p.dbg & 8) ? 0 : TK / 16); ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
                         umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
                         umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
@@ -230,7 +239,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int t = threadIdx.x - 64;     // 0..255
         const mi_epilogue_t& e = p.e;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles && !p.presplit; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * TM;
             // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
             // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
@@ -253,6 +262,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const float4* raw = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
                 uint8_t* hi = smem + s * STAGE_BYTES + A_RAW;
                 uint8_t* lo = hi + A_H;
+                if (p.dbg & 2) {
+                    mbar_arrive(&split[s]);
+                    continue;
+                }
                 // all loads first (the stores below may alias them as far as the compiler knows), then convert + store
                 float4 v[4];
                 float sc[4];
@@ -309,6 +322,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 i3 = (mrow_ok && e.g3) ? (e.g3_idx ? __ldg(e.g3_idx + mrow) : mrow) : 0;
             }
             constexpr int CH = TN / 64;                          // 32-column chunks per warp
+            float rowmax[8];                                     // running max |C| of the 8 rows this lane touches
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rowmax[u] = 0.f;
 #pragma unroll 1
             for (int cc = 0; cc < CH; ++cc) {
                 const int c = hf * CH + cc;
@@ -351,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const bool vec = p.c_vec && (n + 3 < p.N);
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (e.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-#pragma unroll 4
+#pragma unroll
                 for (int rr0 = 0; rr0 < 32; rr0 += 4) {
                     const int rr = rr0 + (lane >> 3);
                     const int m = m0 + q * 32 + rr;
@@ -402,14 +418,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                     }
                     }
-                    if (e.amax_out) {                                  // row max over the 8 lanes that share row rr
-                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
-                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
-                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 4));
-                        if (active && (lane & 7) == 0) atomicMax(reinterpret_cast<unsigned*>(e.amax_out + m), __float_as_uint(rmax));
-                    }
+                    rowmax[rr0 >> 2] = fmaxf(rowmax[rr0 >> 2], rmax);
                 }
                 __syncwarp();
+            }
+            if (e.amax_out) {                                    // one atomic per row per warp: max over the 8 lanes sharing a row
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float rmax = rowmax[u];
+                    rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+                    rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+                    rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 4));
+                    const int m = m0 + q * 32 + u * 4 + (lane >> 3);
+                    if ((lane & 7) == 0 && m < p.M) atomicMax(reinterpret_cast<unsigned*>(e.amax_out + m), __float_as_uint(rmax));
+                }
             }
         }
     }
@@ -465,13 +487,14 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 
 
 template <int STAGES, int TN, int EPI>
-int launch_tc(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw, cudaStream_t s,
-              const TcParams& p) {
+int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi, const void* W_lo, int ldw,
+              cudaStream_t s, const TcParams& p) {
     using C = Cfg<STAGES, TN>;
     static bool attr = false;
     int rc;
-    CUtensorMap mA, mWh, mWl;
-    if ((rc = make_map(&mA, A, M, K, lda, TM, false)) != MI_OK) return rc;
+    CUtensorMap mA, mAl, mWh, mWl;
+    if ((rc = make_map(&mA, A, M, K, lda, TM, p.presplit != 0)) != MI_OK) return rc;
+    if ((rc = make_map(&mAl, p.presplit ? A_lo : A, M, K, lda, TM, p.presplit != 0)) != MI_OK) return rc;
     if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, true)) != MI_OK) return rc;
     if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, true)) != MI_OK) return rc;
     if (!attr) {
@@ -486,7 +509,7 @@ int launch_tc(int M, int N, int K, const float* A, int lda, const void* W_hi, co
     }
     const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM);
     const int grid = (int)(tiles < sms ? tiles : sms);        // persistent: one CTA per SM
-    tc_gemm_kernel<STAGES, TN, EPI><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mWh, mWl, p);
+    tc_gemm_kernel<STAGES, TN, EPI><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -501,14 +524,14 @@ extern "C" int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_
     return MI_OK;
 }
 
-extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
-                          float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
+static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi, const void* W_lo,
+                        int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
     MI_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "bad dimension");
     if (M == 0 || N == 0) return MI_OK;
     MI_CHECK_ARG(A && W_hi && W_lo && C, "null operand");
     MI_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "leading dimension too small");
-    MI_CHECK_ARG(lda % 4 == 0 && ldw % 8 == 0 && mi_host_aligned16(A) && mi_host_aligned16(W_hi) && mi_host_aligned16(W_lo),
-                 "TMA operands need 16-byte aligned rows (lda % 4, ldw % 8)");
+    MI_CHECK_ARG(lda % (A_lo ? 8 : 4) == 0 && ldw % 8 == 0 && mi_host_aligned16(A) && (!A_lo || mi_host_aligned16(A_lo)) &&
+                 mi_host_aligned16(W_hi) && mi_host_aligned16(W_lo), "TMA operands need 16-byte aligned rows (fp32: ld % 4, fp16: ld % 8)");
     int rc = get_encode();
     if (rc != MI_OK) return rc;
     TcParams p;
@@ -531,6 +554,13 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const vo
     if (e.z_in) cv = cv && (e.zin_ld % 4 == 0) && mi_host_aligned16(e.z_in);
     if (e.resid) cv = cv && (e.resid_ld % 4 == 0) && mi_host_aligned16(e.resid);
     p.c_vec = cv;
+    p.presplit = A_lo != nullptr;
+    if (p.presplit) MI_CHECK_ARG(p.e.a_amax == nullptr, "pre-split A carries no row rescaling");
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* d = getenv("MI_TC_DBG"); dbg = d ? atoi(d) : 0; }
+        p.dbg = dbg;
+    }
     // Column-tile width: 128 (two double-buffered {main, correction} accumulator pairs fill the 512 TMEM columns);
     // 64 only for narrow outputs.
     int tn = (N <= 64) ? 64 : 128;
@@ -540,12 +570,23 @@ extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const vo
     const int epi_mode = ((p.e.g1 || p.e.g2 || p.e.g3) ? 1 : 0) | (p.e.z_out ? 2 : 0);
 #define MI_TC_CASE(ST, TNV)                                                                              \
     switch (epi_mode) {                                                                                     \
-        case 0: return launch_tc<ST, TNV, 0>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                    \
-        case 1: return launch_tc<ST, TNV, 1>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                    \
-        case 2: return launch_tc<ST, TNV, 2>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                    \
-        default: return launch_tc<ST, TNV, 3>(M, N, K, A, lda, W_hi, W_lo, ldw, s, p);                   \
+        case 0: return launch_tc<ST, TNV, 0>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
+        case 1: return launch_tc<ST, TNV, 1>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
+        case 2: return launch_tc<ST, TNV, 2>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
+        default: return launch_tc<ST, TNV, 3>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                   \
     }
     if (tn == 128) { MI_TC_CASE(4, 128) }
     MI_TC_CASE(4, 64)
 #undef MI_TC_CASE
+}
+
+extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
+                          float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
+    return tc_gemm_impl(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, C, ldc, epi, stream);
+}
+
+extern "C" int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
+                                   const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
+    MI_CHECK_ARG(A_lo != nullptr, "null operand");
+    return tc_gemm_impl(M, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, C, ldc, epi, stream);
 }

@@ -42,10 +42,13 @@ class _Workspace:
             return torch.empty(*shape, device=dev, dtype=f32)
 
         self.train = train
-        self.phi = buf(E, F6)
+        self.phi = buf(E, F6)                               # fp32 basis: backward (dW_F) and the FFMA path
+        self.phi_hi = torch.empty(E, F6, device=dev, dtype=torch.float16)
+        self.phi_lo = torch.empty(E, F6, device=dev, dtype=torch.float16)
         self.ips = buf(B, 9)
         self.tb = buf(B, H)
-        self.cb = buf(B, H)
+        self.cb2 = torch.zeros(B, 2 * H, device=dev, dtype=f32)   # [C_b | 0]: folded into P by the P|Q GEMM's epilogue
+        self.cb = self.cb2[:, :H]
         self.h0 = buf(N, H)
         self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] * (L + 1)
         self.cat = [buf(N, 2 * H) for _ in range(nl)]
@@ -352,7 +355,9 @@ class CSPNet(nn.Module):
         self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
         self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
         ops.lattice_ip(l, ws.ips, B)
-        ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi)
+        presplit = self.use_tc and (6 * F) % 8 == 0
+        ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
+                         ws.phi_hi if presplit else None, ws.phi_lo if presplit else None)
         for i in range(L):
             q = "l%d." % i
             k = i if train else 0
@@ -368,11 +373,16 @@ class CSPNet(nn.Module):
                 hn.copy_(h_in)
                 torch.maximum(ws.amax_agg[i], h_in.abs().amax(dim=1), out=ws.amax_agg[i])
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
-            self._linear(hn, q + "w_pq", ws.pq, N)
+            # per-crystal term C_b first, folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the
+            # per-edge GEMM then adds two gathered rows instead of three
             ops.lattice_linear(l, W[q + "w_l"], W[q + "b1"], ws.cb, B, H)
-            self._linear(ws.phi, q + "w_f", a1, E,
-                         gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst), (ws.cb, g.edge_graph)],
-                         z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
+            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2, g.node_graph)])
+            epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
+                        z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
+            if presplit:
+                ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, self._hi[q + "w_f"], self._lo[q + "w_f"], a1, M=E, **epi1)
+            else:
+                self._linear(ws.phi, q + "w_f", a1, E, **epi1)
             self._linear(a1, q + "w2", ws.a2, E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU,
                          a_amax=ws.amax_a1[i])
             # scatter-mean over the source node (cspnet.py:79)

@@ -110,6 +110,20 @@ def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_
     return C_
 
 
+def tc_gemm_presplit(A_hi, A_lo, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, resid=None,
+                     act=ACT_NONE, alpha=1.0, amax_out=None):
+    """tc_gemm with A given as fp16 (hi, scaled lo) arrays from its producer.  See mi_tc_gemm_presplit."""
+    for t in (C_, bias, z_out, resid):
+        _f32(t)
+    M = A_hi.shape[0] if M is None else M
+    K = A_hi.shape[1] if K is None else K
+    N = W_hi.shape[0] if N is None else N
+    e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, None)
+    check(lib().mi_tc_gemm_presplit(M, N, K, A_hi.data_ptr(), A_lo.data_ptr(), _ld(A_hi), W_hi.data_ptr(), W_lo.data_ptr(),
+                                    _ld(W_hi), C_.data_ptr(), _ld(C_), C.byref(e), _stream()), "mi_tc_gemm_presplit")
+    return C_
+
+
 def fc_edges(node_off, edge_off, B, N, E, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
     for t in (node_off, edge_off, edge_src, edge_dst, edge_graph, seg_ptr, dst_ptr, dst_perm, node_graph):
         _i32(t)
@@ -117,10 +131,11 @@ def fc_edges(node_off, edge_off, B, N, E, edge_src, edge_dst, edge_graph, seg_pt
                             _p(seg_ptr), _p(dst_ptr), _p(dst_perm), _p(node_graph), _stream()), "mi_fc_edges")
 
 
-def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi):
+def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi, phi_hi=None, phi_lo=None):
     _f32(x), _f32(phi), _f32(cell_off), _f32(frac_diff), _i32(edge_src), _i32(edge_dst)
+    ld = _ld(phi) if phi is not None else _ld(phi_hi)
     check(lib().mi_edge_fourier(_p(x), _p(edge_src), _p(edge_dst), _p(cell_off), E, F, _p(frac_diff), _p(phi),
-                                _ld(phi), _stream()), "mi_edge_fourier")
+                                ld, _p(phi_hi), _p(phi_lo), _stream()), "mi_edge_fourier")
 
 
 def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None):
