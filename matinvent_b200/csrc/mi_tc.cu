@@ -82,13 +82,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 // K-major fp16 operand tile, 64-byte rows, SWIZZLE_64B: 8-row groups of 512 B (SBO), LBO unused (=1),
 // descriptor version 1, layout type 4.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, int sw128 = 0) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((sw128 ? 1024 : 512) >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(sw128 ? 2 : 4) << 61;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -122,7 +122,6 @@ struct TcParams {
     mi_epilogue_t e;
     int c_vec;
     int presplit; // A is given as two fp16 arrays (hi, scaled lo): TMA loads them straight into the operand tiles
-    int dbg;      // MI_TC_DBG (profiling experiments only): 1 = no A loads, 2 = no operand split, 4 = no W loads, 8 = no MMA
 };
 
 // EPI bit 0: row gathers present, bit 1: pre-activation store (training).  bias / SiLU / residual stay runtime flags.
@@ -191,15 +190,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], ((p.dbg & 1) ? 0 : (p.presplit ? 2 * A_H : A_RAW)) + ((p.dbg & 4) ? 0 : 2 * W_H));
+                    mbar_expect_tx(&full[s], (p.presplit ? 2 * A_H : A_RAW) + 2 * W_H);
                     if (p.presplit) {
                         tma_load_2d(st + A_RAW, &mapA, &full[s], kb * TK, m0);
                         tma_load_2d(st + A_RAW + A_H, &mapAlo, &full[s], kb * TK, m0);
-                    } else if (!(p.dbg & 1)) tma_load_2d(st, &mapA, &full[s], kb * TK, m0);
-                    if (!(p.dbg & 4)) {
-                        tma_load_2d(st + A_RAW + 2 * A_H, &mapWhi, &full[s], kb * TK, n0);
-                        tma_load_2d(st + A_RAW + 2 * A_H + W_H, &mapWlo, &full[s], kb * TK, n0);
+                    } else {
+                        tma_load_2d(st, &mapA, &full[s], kb * TK, m0);
                     }
+                    tma_load_2d(st + A_RAW + 2 * A_H, &mapWhi, &full[s], kb * TK, n0);
+                    tma_load_2d(st + A_RAW + 2 * A_H + W_H, &mapWlo, &full[s], kb * TK, n0);
                 }
             }
         }
@@ -219,11 +218,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (!p.presplit) mbar_wait(&split[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    const int sw = (p.dbg & 16) ? 1 : 0;      // timing experiment only (wrong results)
-                    const uint64_t d_ahi = umma_desc(st + A_RAW, sw), d_alo = umma_desc(st + A_RAW + A_H, sw);
-                    const uint64_t d_whi = umma_desc(st + A_RAW + 2 * A_H, sw), d_wlo = umma_desc(st + A_RAW + 2 * A_H + W_H, sw);
+                    const uint64_t d_ahi = umma_desc(st + A_RAW), d_alo = umma_desc(st + A_RAW + A_H);
+                    const uint64_t d_whi = umma_desc(st + A_RAW + 2 * A_H), d_wlo = umma_desc(st + A_RAW + 2 * A_H + W_H);
 #pragma unroll
-                    for (int k = 0; k < ((p.dbg & 8) ? 0 : TK / 16); ++k) {
+                    for (int k = 0; k < TK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
                         umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
                         umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
@@ -262,10 +260,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const float4* raw = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
                 uint8_t* hi = smem + s * STAGE_BYTES + A_RAW;
                 uint8_t* lo = hi + A_H;
-                if (p.dbg & 2) {
-                    mbar_arrive(&split[s]);
-                    continue;
-                }
                 // all loads first (the stores below may alias them as far as the compiler knows), then convert + store
                 float4 v[4];
                 float sc[4];
@@ -364,61 +358,87 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 __syncwarp();
                 const int col4 = (lane & 7) * 4;
                 const int n = nb + col4;
-                const bool vec = p.c_vec && (n + 3 < p.N);
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                if (p.c_vec && nb + 32 <= p.N) {
+                    // ---- fast path: whole chunk in range, 16-byte accesses.  Software-pipelined in two batches of four
+                    // row groups: all gather / residual loads of a batch are issued before any arithmetic or store, so
+                    // their L2 round trips overlap (the compiler will not move loads across the stores by itself).
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
 #pragma unroll
-                for (int rr0 = 0; rr0 < 32; rr0 += 4) {
-                    const int rr = rr0 + (lane >> 3);
-                    const int m = m0 + q * 32 + rr;
-                    int r1 = 0, r2 = 0, r3 = 0;
-                    if (EPI & 1) {
-                        r1 = __shfl_sync(0xffffffffu, i1, rr);
-                        r2 = __shfl_sync(0xffffffffu, i2, rr);
-                        r3 = __shfl_sync(0xffffffffu, i3, rr);
-                    }
-                    const bool active = (m < p.M) && (n < p.N);
-                    float rmax = 0.f;
-                    if (active) {
-                    const float2 xa = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4);
-                    const float2 xb = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4 + 2);
-                    float x[4] = {xa.x, xa.y, xb.x, xb.y};
-                    float* crow = p.C + (long long)m * p.ldc + n;
-                    if (vec) {
-                        x[0] += bias4.x; x[1] += bias4.y; x[2] += bias4.z; x[3] += bias4.w;
-                        if (EPI & 1) {
-                            if (e.g1) { float4 tq = __ldg(reinterpret_cast<const float4*>(e.g1 + (long long)r1 * e.g1_ld + n)); x[0] += tq.x; x[1] += tq.y; x[2] += tq.z; x[3] += tq.w; }
-                            if (e.g2) { float4 tq = __ldg(reinterpret_cast<const float4*>(e.g2 + (long long)r2 * e.g2_ld + n)); x[0] += tq.x; x[1] += tq.y; x[2] += tq.z; x[3] += tq.w; }
-                            if (e.g3) { float4 tq = __ldg(reinterpret_cast<const float4*>(e.g3 + (long long)r3 * e.g3_ld + n)); x[0] += tq.x; x[1] += tq.y; x[2] += tq.z; x[3] += tq.w; }
-                        }
-                        if (EPI & 2) *reinterpret_cast<float4*>(e.z_out + (long long)m * e.z_ld + n) = make_float4(x[0], x[1], x[2], x[3]);
-                        if (e.act == MI_ACT_SILU) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) x[u] = silu_fast(x[u]);
-                        }
-                        if (e.resid) { float4 tq = __ldg(reinterpret_cast<const float4*>(e.resid + (long long)m * e.resid_ld + n)); x[0] += tq.x; x[1] += tq.y; x[2] += tq.z; x[3] += tq.w; }
-                        *reinterpret_cast<float4*>(crow) = make_float4(x[0], x[1], x[2], x[3]);
-                        rmax = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
-                    } else {
+                    for (int hb = 0; hb < 2; ++hb) {
+                        float4 ga[4], gb[4], gc[4], gr[4];
+                        int mm[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            if (n + u >= p.N) continue;
-                            float y = x[u];
-                            if (e.bias) y += __ldg(e.bias + n + u);
+                            const int rr = (hb * 4 + u) * 4 + (lane >> 3);
+                            const int m = m0 + q * 32 + rr;
+                            mm[u] = m;
+                            const bool ok = m < p.M;
+                            ga[u] = gb[u] = gc[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (EPI & 1) {
-                                if (e.g1) y += __ldg(e.g1 + (long long)r1 * e.g1_ld + n + u);
-                                if (e.g2) y += __ldg(e.g2 + (long long)r2 * e.g2_ld + n + u);
-                                if (e.g3) y += __ldg(e.g3 + (long long)r3 * e.g3_ld + n + u);
+                                const int r1 = __shfl_sync(0xffffffffu, i1, rr), r2 = __shfl_sync(0xffffffffu, i2, rr),
+                                          r3 = __shfl_sync(0xffffffffu, i3, rr);
+                                if (ok && e.g1) ga[u] = __ldg(reinterpret_cast<const float4*>(e.g1 + (long long)r1 * e.g1_ld + n));
+                                if (ok && e.g2) gb[u] = __ldg(reinterpret_cast<const float4*>(e.g2 + (long long)r2 * e.g2_ld + n));
+                                if (ok && e.g3) gc[u] = __ldg(reinterpret_cast<const float4*>(e.g3 + (long long)r3 * e.g3_ld + n));
                             }
-                            if (EPI & 2) e.z_out[(long long)m * e.z_ld + n + u] = y;
-                            if (e.act == MI_ACT_SILU) y = silu_fast(y);
-                            if (e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
-                            crow[u] = y;
-                            rmax = fmaxf(rmax, fabsf(y));
+                            if (ok && e.resid) gr[u] = __ldg(reinterpret_cast<const float4*>(e.resid + (long long)m * e.resid_ld + n));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int rr = (hb * 4 + u) * 4 + (lane >> 3);
+                            const int m = mm[u];
+                            if (m >= p.M) continue;
+                            const float2 xa = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4);
+                            const float2 xb = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4 + 2);
+                            float x[4] = {xa.x + bias4.x, xa.y + bias4.y, xb.x + bias4.z, xb.y + bias4.w};
+                            if (EPI & 1) {
+                                x[0] += ga[u].x + gb[u].x + gc[u].x; x[1] += ga[u].y + gb[u].y + gc[u].y;
+                                x[2] += ga[u].z + gb[u].z + gc[u].z; x[3] += ga[u].w + gb[u].w + gc[u].w;
+                            }
+                            if (EPI & 2) *reinterpret_cast<float4*>(e.z_out + (long long)m * e.z_ld + n) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (e.act == MI_ACT_SILU) {
+#pragma unroll
+                                for (int v4 = 0; v4 < 4; ++v4) x[v4] = silu_fast(x[v4]);
+                            }
+                            x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w;
+                            *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
+                            rowmax[hb * 4 + u] = fmaxf(rowmax[hb * 4 + u], fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
                         }
                     }
+                } else {
+                    // ---- generic path (ragged N or unaligned rows): scalar, bounds-checked
+#pragma unroll 1
+                    for (int rr0 = 0; rr0 < 32; rr0 += 4) {
+                        const int rr = rr0 + (lane >> 3);
+                        const int m = m0 + q * 32 + rr;
+                        int r1 = 0, r2 = 0, r3 = 0;
+                        if (EPI & 1) {
+                            r1 = __shfl_sync(0xffffffffu, i1, rr);
+                            r2 = __shfl_sync(0xffffffffu, i2, rr);
+                            r3 = __shfl_sync(0xffffffffu, i3, rr);
+                        }
+                        float rmax = 0.f;
+                        if (m < p.M) {
+                            float* crow = p.C + (long long)m * p.ldc + n;
+                            for (int u = 0; u < 4; ++u) {
+                                if (n + u >= p.N) continue;
+                                float y = ebuf[rr * EP + col4 + u];
+                                if (e.bias) y += __ldg(e.bias + n + u);
+                                if (EPI & 1) {
+                                    if (e.g1) y += __ldg(e.g1 + (long long)r1 * e.g1_ld + n + u);
+                                    if (e.g2) y += __ldg(e.g2 + (long long)r2 * e.g2_ld + n + u);
+                                    if (e.g3) y += __ldg(e.g3 + (long long)r3 * e.g3_ld + n + u);
+                                }
+                                if (EPI & 2) e.z_out[(long long)m * e.z_ld + n + u] = y;
+                                if (e.act == MI_ACT_SILU) y = silu_fast(y);
+                                if (e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
+                                crow[u] = y;
+                                rmax = fmaxf(rmax, fabsf(y));
+                            }
+                        }
+                        rowmax[rr0 >> 2] = fmaxf(rowmax[rr0 >> 2], rmax);
                     }
-                    rowmax[rr0 >> 2] = fmaxf(rowmax[rr0 >> 2], rmax);
                 }
                 __syncwarp();
             }
@@ -556,11 +576,6 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     p.c_vec = cv;
     p.presplit = A_lo != nullptr;
     if (p.presplit) MI_CHECK_ARG(p.e.a_amax == nullptr, "pre-split A carries no row rescaling");
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char* d = getenv("MI_TC_DBG"); dbg = d ? atoi(d) : 0; }
-        p.dbg = dbg;
-    }
     // Column-tile width: 128 (two double-buffered {main, correction} accumulator pairs fill the 512 TMEM columns);
     // 64 only for narrow outputs.
     int tn = (N <= 64) ? 64 : 128;
