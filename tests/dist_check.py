@@ -49,6 +49,29 @@ def main():
     assert frac_big < 1e-3 and float(d.mean()) < 1e-7, (frac_big, float(d.mean()))
     for a, b in zip(logs_multi, logs_single):
         assert abs(a - b) < 1e-4 * abs(b) + 1e-9, (logs_multi, logs_single)
+    # sharded sampling through the pipeline mirror: every rank samples its share, all ranks end up with the full list
+    from matinvent_b200.pipeline.mat_invent import MatInvent
+    import numpy as np
+
+    class _Suite:
+        sample_cfg, finetune_cfg = dict(batch_size=6, num_batches=1), dict(batch_size=4)
+        def get_sampler(self):
+            from matinvent_b200.models.diffcsp import DiffCSPSampler
+            return DiffCSPSampler(batch_size=6, num_batches=1)
+        def load_model(self):
+            return build_module(hp, gs["sd"], gs["sigmas_norm"], device=dev)
+    np.random.seed(100 + rank)
+    torch.manual_seed(100 + rank)
+    import tempfile
+    pipe = MatInvent(rl_epoch=1, model_suite=_Suite(), reward=None, sample_cfg={}, finetune_cfg={}, save_dir=tempfile.mkdtemp(),
+                     save_freq=1, device=str(dev))
+    data, strucs, _, _ = pipe.sample_step()
+    assert len(data) == 6 and len(strucs) == 6, len(data)
+    sizes = torch.tensor([int(d.num_atoms) for d in data], device=dev)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    for t in all_sizes[1:]:
+        assert torch.equal(all_sizes[0], t), "ranks disagree on the gathered sample list"
     if rank == 0:
         print("DIST_CHECK_OK", logs_multi)
     dist.destroy_process_group()
