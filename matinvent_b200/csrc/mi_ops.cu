@@ -73,10 +73,59 @@ __global__ void fc_edges_kernel(const int* __restrict__ node_off, const int* __r
 }
 
 // ------------------------------------------------------------------------------------ Fourier basis
+// thread = (edge, coordinate c, 4 consecutive frequencies): four independent sincos chains per thread (ILP) and
+// 8/16-byte stores; the frequency block of a coordinate is 4-aligned because F % 4 == 0 on this path.
 __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __restrict__ src,
                                     const int* __restrict__ dst, const float* __restrict__ cell_off,
                                     int E, int F, float* __restrict__ frac_diff, float* __restrict__ phi,
                                     int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int F3 = 3 * F, Q = F3 >> 2;
+    if (t >= (long long)E * Q) return;
+    int e = (int)(t / Q);
+    int col = (int)(t - (long long)e * Q) << 2;
+    int c = col / F, k = col - c * F;
+    int i = __ldg(src + e), j = __ldg(dst + e);
+    float d = __fsub_rn(__ldg(x + 3 * j + c), __ldg(x + 3 * i + c));
+    if (cell_off) d = __fadd_rn(d, __ldg(cell_off + 3 * (long long)e + c));   // knn: un-wrapped (cspnet.py:252-257)
+    else d = mi_mod1(d);                                                      // fc: (x_j - x_i) % 1 (cspnet.py:242)
+    if (k == 0 && frac_diff) frac_diff[3 * (long long)e + c] = d;
+    float sv[4], cv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        float freq = __fmul_rn((float)(k + u), 6.2831855f);   // fl32(2*pi) * fl32(k)   (cspnet.py:18)
+        sincosf(__fmul_rn(d, freq), &sv[u], &cv[u]);
+    }
+    const long long o = (long long)e * ld_phi + col;
+    if (phi) {
+        *reinterpret_cast<float4*>(phi + o) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+        *reinterpret_cast<float4*>(phi + o + F3) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+    }
+    if (phi_hi) {      // operand form of mi_tc_gemm_presplit: fp16 head + 2^11-scaled fp16 tail (|Phi| <= 1: no rescaling)
+        __half2 hs0 = __floats2half2_rn(sv[0], sv[1]), hs1 = __floats2half2_rn(sv[2], sv[3]);
+        __half2 hc0 = __floats2half2_rn(cv[0], cv[1]), hc1 = __floats2half2_rn(cv[2], cv[3]);
+        float2 fs0 = __half22float2(hs0), fs1 = __half22float2(hs1), fc0 = __half22float2(hc0), fc1 = __half22float2(hc1);
+        __half2 ls0 = __floats2half2_rn((sv[0] - fs0.x) * 2048.0f, (sv[1] - fs0.y) * 2048.0f);
+        __half2 ls1 = __floats2half2_rn((sv[2] - fs1.x) * 2048.0f, (sv[3] - fs1.y) * 2048.0f);
+        __half2 lc0 = __floats2half2_rn((cv[0] - fc0.x) * 2048.0f, (cv[1] - fc0.y) * 2048.0f);
+        __half2 lc1 = __floats2half2_rn((cv[2] - fc1.x) * 2048.0f, (cv[3] - fc1.y) * 2048.0f);
+        auto st2 = [](__half* p, __half2 a, __half2 b) {
+            uint2 v;
+            v.x = *reinterpret_cast<unsigned*>(&a);
+            v.y = *reinterpret_cast<unsigned*>(&b);
+            *reinterpret_cast<uint2*>(p) = v;
+        };
+        st2(phi_hi + o, hs0, hs1);
+        st2(phi_hi + o + F3, hc0, hc1);
+        st2(phi_lo + o, ls0, ls1);
+        st2(phi_lo + o + F3, lc0, lc1);
+    }
+}
+// scalar variant for F % 4 != 0 (thread = one (edge, column))
+__global__ void edge_fourier_kernel_scalar(const float* __restrict__ x, const int* __restrict__ src,
+                                           const int* __restrict__ dst, const float* __restrict__ cell_off,
+                                           int E, int F, float* __restrict__ frac_diff, float* __restrict__ phi,
+                                           int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int F3 = 3 * F;
     if (t >= (long long)E * F3) return;
@@ -85,20 +134,18 @@ __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __re
     int c = col / F, k = col - c * F;
     int i = __ldg(src + e), j = __ldg(dst + e);
     float d = __fsub_rn(__ldg(x + 3 * j + c), __ldg(x + 3 * i + c));
-    if (cell_off) d = __fadd_rn(d, __ldg(cell_off + 3 * (long long)e + c));   // knn: un-wrapped (cspnet.py:252-257)
-    else d = mi_mod1(d);                                                      // fc: (x_j - x_i) % 1 (cspnet.py:242)
+    if (cell_off) d = __fadd_rn(d, __ldg(cell_off + 3 * (long long)e + c));
+    else d = mi_mod1(d);
     if (k == 0 && frac_diff) frac_diff[3 * (long long)e + c] = d;
-    float freq = __fmul_rn((float)k, 6.2831855f);   // fl32(2*pi) * fl32(k)   (cspnet.py:18)
-    float arg = __fmul_rn(d, freq);
+    float freq = __fmul_rn((float)k, 6.2831855f);
     float s, co;
-    sincosf(arg, &s, &co);
+    sincosf(__fmul_rn(d, freq), &s, &co);
+    const long long o = (long long)e * ld_phi;
     if (phi) {
-        float* row = phi + (long long)e * ld_phi;
-        row[col] = s;
-        row[F3 + col] = co;
+        phi[o + col] = s;
+        phi[o + F3 + col] = co;
     }
-    if (phi_hi) {      // operand form of mi_tc_gemm_presplit: fp16 head + 2^11-scaled fp16 tail (|Phi| <= 1: no rescaling)
-        const long long o = (long long)e * ld_phi;
+    if (phi_hi) {
         __half hs = __float2half_rn(s), hc = __float2half_rn(co);
         phi_hi[o + col] = hs;
         phi_hi[o + F3 + col] = hc;
@@ -683,9 +730,16 @@ extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* e
     MI_CHECK_ARG(E >= 0 && F > 0 && ld_phi >= 6 * F, "bad sizes");
     if (E == 0) return MI_OK;
     MI_CHECK_ARG(x && edge_src && edge_dst && (phi || phi_hi) && ((phi_hi == nullptr) == (phi_lo == nullptr)), "null pointer");
-    long long n = (long long)E * 3 * F;
-    edge_fourier_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F,
-                                                                              frac_diff, phi, ld_phi, (__half*)phi_hi, (__half*)phi_lo);
+    const bool vec = (F % 4 == 0) && (ld_phi % 4 == 0) && (!phi || mi_host_aligned16(phi)) && (!phi_hi || (mi_host_aligned16(phi_hi) && mi_host_aligned16(phi_lo)));
+    if (vec) {
+        long long n = (long long)E * (3 * F / 4);
+        edge_fourier_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi,
+                                                                                  ld_phi, (__half*)phi_hi, (__half*)phi_lo);
+    } else {
+        long long n = (long long)E * 3 * F;
+        edge_fourier_kernel_scalar<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F, frac_diff,
+                                                                                         phi, ld_phi, (__half*)phi_hi, (__half*)phi_lo);
+    }
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
