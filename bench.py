@@ -276,16 +276,24 @@ def main():
     t_g1 = statistics.mean(a.elapsed_time(b) for a, b, c in evs[HP["num_layers"]:]) * 1e3      # us
     t_g2 = statistics.mean(b.elapsed_time(c) for a, b, c in evs[HP["num_layers"]:]) * 1e3
     fl_pair = 2 * g.E * (F6 * H + H * H)
+    fl_g1 = 2 * g.E * F6 * H
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    ach = fl_pair / t_pair / 1e12
+    ach = fl_g1 / (t_g1 * 1e-6) / 1e12
+    ach_pair = fl_pair / t_pair / 1e12
     kname = "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)"
-    roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM pair Phi.W_F^T + gathers + SiLU, then .W_2^T + SiLU",
-                    achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=None,
+    # DRAM traffic of this launch from the committed ncu --set full capture of the default workload
+    # (profiles/r1_final_tc_gemm_ncu_raw.csv: dram__bytes_read.sum 118.8 MB + dram__bytes_write.sum 36.0 MB)
+    traffic = 154.8e6 if (dec.use_tc and g.E == 34445) else None
+    roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM 1 (Phi.W_F^T + 2 gathered rows + SiLU), the largest launch",
+                    achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
+                    flop_per_launch=fl_g1, us_per_launch=t_g1,
+                    algorithmic_bytes_per_launch=2 * 2 * g.E * F6 + 4 * g.E * H + 2 * 2 * H * F6 + 2 * 4 * g.N * 2 * H,
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    note="achieved = algorithmic FP32 FLOPs / time; FP32-grade accuracy costs 3 fp16 MMAs per product (x = hi + "
-                         "2^-11 lo), so the ceiling of this number is peak/3 (1e-4 parity over 2000 chained forwards rules out "
-                         "plain TF32/BF16/FP16 inputs); share of step = %.2f" % (2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
+                    note="achieved = algorithmic FP32 FLOPs / CUDA-event time of the launch; FP32-grade accuracy costs 3 fp16 MMAs per "
+                         "product (x = hi + 2^-11 lo), so the ceiling of frac is 1/3 (1e-4 parity over 2000 chained forwards rules out "
+                         "plain TF32/BF16/FP16 inputs); edge GEMM pair (this launch + the K=512 one): %.1f TFLOP/s, share of step = %.2f"
+                         % (ach_pair, 2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
                     mma_tflops=3 * ach, frac_mma_of_peak=3 * ach / peak_tf, us_gemm1=t_g1, us_gemm2=t_g2)
     # the edge-scatter (segment-mean) kernel against the HBM roofline, in isolation, L2 flushed between launches
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -302,8 +310,11 @@ def main():
     seg_bytes = 4 * g.E * H + 4 * (g.N + 1) + 4 * g.N * H
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline_scatter = dict(bound="hbm", kernel="segment_reduce_kernel (edge scatter-mean)", achieved=seg_bytes / t_seg / 1e9,
-                            peak=hbm_peak, unit="GB/s", frac=seg_bytes / t_seg / 1e9 / hbm_peak, traffic=None,
-                            bytes_per_launch=seg_bytes, us_per_launch=t_seg * 1e6)
+                            peak=hbm_peak, unit="GB/s", frac=seg_bytes / t_seg / 1e9 / hbm_peak,
+                            traffic=71.8e6 if g.E == 34445 else None,      # ncu: profiles/r1_final_segment_reduce_ncu_raw.csv
+                            bytes_per_launch=seg_bytes, us_per_launch=t_seg * 1e6,
+                            note="in isolation, L2 flushed between launches; 76 MB is ~2x the DRAM latency floor of a launch: the "
+                                 "same kernel reaches 77 % at 4x the batch (scripts/bench_seg.py, profiles/README.md)")
 
     # ---- e2e through the plugin call, host buffers, copies inside the timed region
     e2e = None
