@@ -70,19 +70,33 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
              int ldb, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
 
 /* Tensor-core variant for the forward dense blocks (A [M,K] and W [N,K] both K-contiguous, i.e.
- * transA = 0, transB = 1): FP32-grade product by split-precision FP16 on tcgen05 (x = x_hi + 2^-11 x_lo, three
- * MMAs per k-slice, TMA-staged swizzled operand tiles, two TMEM accumulators), same epilogue contract as
+ * transA = 0, transB = 1): FP32-grade product by split-precision FP16 on tcgen05 (x = x_hi + x_lo, three
+ * MMAs per k-slice, TMA-staged swizzled operand tiles, TMEM accumulators), same epilogue contract as
  * mi_sgemm (no split-K).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
- * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo,
- * and |W| < 65504; A rows larger than 2^15 need epi->a_amax (see mi_epilogue_t). */
-int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_stream_t stream);
+ * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo.
+ *
+ * Two operand formats (flags):
+ *   0             hi = fp16(x), lo = fp16((x - hi) * 2^11); 128-column tiles with a separate, 2^11-scaled
+ *                 correction accumulator (lowest rounding error).  Needs |W| < 65504; A rows larger than
+ *                 2^15 need epi->a_amax (see mi_epilogue_t).
+ *   MI_TC_MERGED  hi = fp16(s x), lo = fp16(s x - hi) with s a power of two that brings max |x| into
+ *                 [2^14, 2^15) (per tensor for W — the caller folds 1/s into epi->alpha —, per row for A via
+ *                 epi->a_amax, which is then mandatory): all three products go into ONE accumulator, so a
+ *                 128x256 tile double-buffers in TMEM; half the operand traffic per flop, about 3x the
+ *                 (still ~1e-6 relative) rounding error.
+ * mi_f16_split(w, hi, lo, n, scale, lo_scale): hi = fp16(scale * w), lo = fp16((scale * w - hi) * lo_scale);
+ * (1, 2048) is the format of flags = 0, (s, 1) the merged one. */
+#define MI_TC_MERGED 1
+int mi_f16_split(const float* w, void* hi, void* lo, long long n, float scale, float lo_scale, mi_stream_t stream);
 int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
-               float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
-/* Same, with A already split by its producer into fp16 (hi, 2^11-scaled lo) arrays of leading dimension lda
- * (lda % 8 == 0): the operand tiles are loaded by TMA directly, no in-kernel split (mi_edge_fourier emits this
- * form of the Fourier basis, which is bounded by 1 and needs no row rescaling). */
+               float* C, int ldc, const mi_epilogue_t* epi, int flags, mi_stream_t stream);
+/* Same, with A already split by its producer into fp16 (hi, lo) arrays of leading dimension lda
+ * (lda % 8 == 0) in the format `flags` names: the operand tiles are loaded by TMA directly, no in-kernel split
+ * and no row rescaling (mi_edge_fourier emits this form of the Fourier basis, which is bounded by 1; in the
+ * merged format it is scaled by 2^14 and the caller folds 2^-14 into epi->alpha). */
 int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
-                        const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream);
+                        const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, int flags,
+                        mi_stream_t stream);
 
 /* ---------------------------------------------------------------- graph construction
  * Fully-connected intra-crystal edges, row-major by (i, j) incl. i == j
@@ -100,10 +114,11 @@ int mi_fc_edges(const int* node_off, const int* edge_off, int B, int N, int E, i
  * followed by the Fourier basis Phi[e] = [sin(d_c * 2 pi k)]_{c<3,k<F} || [cos(...)] (cspnet.py:12-24),
  * evaluated with the reference's fp32 arithmetic (arg = d * float(2 pi k)).
  * frac_diff (nullable) [E,3]; phi (nullable) [E, 6F] fp32 with leading dimension ld_phi; phi_hi / phi_lo
- * (nullable pair) the same matrix as fp16 head + 2^11-scaled tail for mi_tc_gemm_presplit (same ld). */
+ * (nullable pair) the same matrix split for mi_tc_gemm_presplit (same ld): phi_hi = fp16(op_scale * Phi),
+ * phi_lo = fp16((op_scale * Phi - phi_hi) * lo_scale) — (1, 2048) or, merged format, (2^14, 1). */
 int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, const float* cell_off,
                     int E, int F, float* frac_diff, float* phi, int ld_phi, void* phi_hi, void* phi_lo,
-                    mi_stream_t stream);
+                    float op_scale, float lo_scale, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- segment reductions
  * out[s][:] = scale_s * sum_{k in [ptr[s], ptr[s+1])} X[perm ? perm[k] : k][:]

@@ -30,11 +30,11 @@ PROTOTYPES = {
     "mi_version": [],
     "mi_device_info": [C.POINTER(i), C.POINTER(i), C.POINTER(i)],
     "mi_sgemm": [i, i, i, i, i, p, i, p, i, p, i, C.POINTER(Epilogue), p],
-    "mi_f16_split": [p, p, p, ll, p],
-    "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
-    "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), p],
+    "mi_f16_split": [p, p, p, ll, f, f, p],
+    "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
+    "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
-    "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, p],
+    "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, f, f, p],
     "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p],
     "mi_colsum": [p, i, i, i, p, i, p],

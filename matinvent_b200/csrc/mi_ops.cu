@@ -78,7 +78,8 @@ __global__ void fc_edges_kernel(const int* __restrict__ node_off, const int* __r
 __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __restrict__ src,
                                     const int* __restrict__ dst, const float* __restrict__ cell_off,
                                     int E, int F, float* __restrict__ frac_diff, float* __restrict__ phi,
-                                    int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo) {
+                                    int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo,
+                                    float op_scale, float lo_scale) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int F3 = 3 * F, Q = F3 >> 2;
     if (t >= (long long)E * Q) return;
@@ -102,13 +103,15 @@ __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __re
         *reinterpret_cast<float4*>(phi + o + F3) = make_float4(cv[0], cv[1], cv[2], cv[3]);
     }
     if (phi_hi) {      // operand form of mi_tc_gemm_presplit: fp16 head + 2^11-scaled fp16 tail (|Phi| <= 1: no rescaling)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { sv[u] *= op_scale; cv[u] *= op_scale; }
         __half2 hs0 = __floats2half2_rn(sv[0], sv[1]), hs1 = __floats2half2_rn(sv[2], sv[3]);
         __half2 hc0 = __floats2half2_rn(cv[0], cv[1]), hc1 = __floats2half2_rn(cv[2], cv[3]);
         float2 fs0 = __half22float2(hs0), fs1 = __half22float2(hs1), fc0 = __half22float2(hc0), fc1 = __half22float2(hc1);
-        __half2 ls0 = __floats2half2_rn((sv[0] - fs0.x) * 2048.0f, (sv[1] - fs0.y) * 2048.0f);
-        __half2 ls1 = __floats2half2_rn((sv[2] - fs1.x) * 2048.0f, (sv[3] - fs1.y) * 2048.0f);
-        __half2 lc0 = __floats2half2_rn((cv[0] - fc0.x) * 2048.0f, (cv[1] - fc0.y) * 2048.0f);
-        __half2 lc1 = __floats2half2_rn((cv[2] - fc1.x) * 2048.0f, (cv[3] - fc1.y) * 2048.0f);
+        __half2 ls0 = __floats2half2_rn((sv[0] - fs0.x) * lo_scale, (sv[1] - fs0.y) * lo_scale);
+        __half2 ls1 = __floats2half2_rn((sv[2] - fs1.x) * lo_scale, (sv[3] - fs1.y) * lo_scale);
+        __half2 lc0 = __floats2half2_rn((cv[0] - fc0.x) * lo_scale, (cv[1] - fc0.y) * lo_scale);
+        __half2 lc1 = __floats2half2_rn((cv[2] - fc1.x) * lo_scale, (cv[3] - fc1.y) * lo_scale);
         auto st2 = [](__half* p, __half2 a, __half2 b) {
             uint2 v;
             v.x = *reinterpret_cast<unsigned*>(&a);
@@ -125,7 +128,8 @@ __global__ void edge_fourier_kernel(const float* __restrict__ x, const int* __re
 __global__ void edge_fourier_kernel_scalar(const float* __restrict__ x, const int* __restrict__ src,
                                            const int* __restrict__ dst, const float* __restrict__ cell_off,
                                            int E, int F, float* __restrict__ frac_diff, float* __restrict__ phi,
-                                           int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo) {
+                                           int ld_phi, __half* __restrict__ phi_hi, __half* __restrict__ phi_lo,
+                                           float op_scale, float lo_scale) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int F3 = 3 * F;
     if (t >= (long long)E * F3) return;
@@ -146,11 +150,13 @@ __global__ void edge_fourier_kernel_scalar(const float* __restrict__ x, const in
         phi[o + F3 + col] = co;
     }
     if (phi_hi) {
+        s *= op_scale;
+        co *= op_scale;
         __half hs = __float2half_rn(s), hc = __float2half_rn(co);
         phi_hi[o + col] = hs;
         phi_hi[o + F3 + col] = hc;
-        phi_lo[o + col] = __float2half_rn((s - __half2float(hs)) * 2048.0f);
-        phi_lo[o + F3 + col] = __float2half_rn((co - __half2float(hc)) * 2048.0f);
+        phi_lo[o + col] = __float2half_rn((s - __half2float(hs)) * lo_scale);
+        phi_lo[o + F3 + col] = __float2half_rn((co - __half2float(hc)) * lo_scale);
     }
 }
 
@@ -726,7 +732,7 @@ extern "C" int mi_fc_edges(const int* node_off, const int* edge_off, int B, int 
 
 extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, const float* cell_off,
                                int E, int F, float* frac_diff, float* phi, int ld_phi, void* phi_hi, void* phi_lo,
-                               mi_stream_t stream) {
+                               float op_scale, float lo_scale, mi_stream_t stream) {
     MI_CHECK_ARG(E >= 0 && F > 0 && ld_phi >= 6 * F, "bad sizes");
     if (E == 0) return MI_OK;
     MI_CHECK_ARG(x && edge_src && edge_dst && (phi || phi_hi) && ((phi_hi == nullptr) == (phi_lo == nullptr)), "null pointer");
@@ -734,11 +740,11 @@ extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* e
     if (vec) {
         long long n = (long long)E * (3 * F / 4);
         edge_fourier_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi,
-                                                                                  ld_phi, (__half*)phi_hi, (__half*)phi_lo);
+                                                                                  ld_phi, (__half*)phi_hi, (__half*)phi_lo, op_scale, lo_scale);
     } else {
         long long n = (long long)E * 3 * F;
         edge_fourier_kernel_scalar<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(x, edge_src, edge_dst, cell_off, E, F, frac_diff,
-                                                                                         phi, ld_phi, (__half*)phi_hi, (__half*)phi_lo);
+                                                                                         phi, ld_phi, (__half*)phi_hi, (__half*)phi_lo, op_scale, lo_scale);
     }
     MI_CHECK_LAUNCH();
     return MI_OK;

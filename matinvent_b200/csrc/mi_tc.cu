@@ -33,7 +33,12 @@ namespace {
 constexpr int TM = 128;                              // CTA tile rows; columns TN in {128, 64} (template)
 constexpr int TC_THREADS = 576;   // w0 TMA, w1 MMA, w2..9 operand split, w10..17 epilogue
 constexpr int TK = 32;                               // k-block: 32 elements = 128 B of fp32, 64 B of fp16
-template <int STAGES, int TN>
+// MERGED = 0: two accumulators per tile (main, 2^11-scaled correction), TN <= 128.
+// MERGED = 1: one accumulator per tile, operands carry an UNSCALED fp16 tail (both operands are pre-scaled by
+//             powers of two into [2^14, 2^15) so the tail stays in fp16's useful range): TN = 256 fits the double
+//             buffer, halving operand bytes and split work per flop at ~2.7x the (still FP32-grade) rounding error,
+//             because three times as many truncating accumulations go into the one accumulator.
+template <int STAGES, int TN, int MERGED = 0>
 struct Cfg {
     static constexpr int A_RAW = TM * TK * 4;                     // 16 KB fp32 tile (TMA, SWIZZLE_128B)
     static constexpr int A_H = TM * TK * 2;                       // 8 KB fp16 tile (SWIZZLE_64B), x2 (hi, lo)
@@ -42,7 +47,7 @@ struct Cfg {
     static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
     static constexpr int EBUF_BYTES = 8 * 32 * EPITCH * 4;        // per-warp transpose buffers of the epilogue
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 128 /*barriers*/ + 128 /*row exponents*/;
-    static constexpr uint32_t ACC_COLS = 2 * TN;                  // main + correction accumulators of one tile
+    static constexpr uint32_t ACC_COLS = MERGED ? TN : 2 * TN;    // accumulator columns of one tile
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;           // double buffered: tile t+1 accumulates while t drains
     // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
@@ -108,13 +113,28 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // the epilogue is issue/latency bound otherwise.
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // x -> (fp16(x), fp16((x - fp16(x)) * 2^11)) packed for two consecutive elements
+template <int MERGED>
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     __half2 h = __floats2half2_rn(x0, x1);
     float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+    const float ls = MERGED ? 1.0f : LO_SCALE;
+    __half2 l = __floats2half2_rn((x0 - hf.x) * ls, (x1 - hf.y) * ls);
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+
+#ifdef MI_TC_TRACE
+// Developer instrumentation (scripts/trace_tc.py builds a separate library with -DMI_TC_TRACE; never in the product
+// build): per-CTA, per-tile SM clock stamps of the pipeline roles.
+constexpr int TR_TILES = 8, TR_SLOTS = 24;
+__device__ long long g_trace[160 * TR_TILES * TR_SLOTS];
+#define TRACE(tileidx, slot)                                                                                   \
+    do {                                                                                                       \
+        if ((tileidx) < TR_TILES) g_trace[(blockIdx.x * TR_TILES + (tileidx)) * TR_SLOTS + (slot)] = clock64(); \
+    } while (0)
+#else
+#define TRACE(tileidx, slot) do {} while (0)
+#endif
 
 struct TcParams {
     int M, N, K;
@@ -125,15 +145,16 @@ struct TcParams {
 };
 
 // EPI bit 0: row gathers present, bit 1: pre-activation store (training).  bias / SiLU / residual stay runtime flags.
-template <int STAGES, int TN, int EPI>
+template <int STAGES, int TN, int EPI, int MERGED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so the CTAs that share an A row
     // block run at the same time and hit it in L2).  Pipeline counters run across tiles, so the producer already
     // streams the next tile's first stages while this tile's epilogue drains TMEM.
-    using C = Cfg<STAGES, TN>;
+    using C = Cfg<STAGES, TN, MERGED>;
     constexpr uint32_t TMEM_COLS = C::TMEM_COLS, IDESC = C::IDESC;
+    constexpr uint32_t CORR = MERGED ? 0 : TN;            // column offset of the correction accumulator
     constexpr int A_RAW = C::A_RAW, A_H = C::A_H, W_H = C::W_H, STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
     float* ebuf_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // 8 warps x 32 x 36 floats
@@ -182,13 +203,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            uint32_t it = 0, tcount = 0;
+            TRACE(0, 14);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
                 const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
+                    if (kb == 0) TRACE(tcount, 0);
                     uint8_t* st = smem + s * STAGE_BYTES;
                     mbar_expect_tx(&full[s], (p.presplit ? 2 * A_H : A_RAW) + 2 * W_H);
                     if (p.presplit) {
@@ -210,12 +233,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const uint32_t ab = tcount & 1;                  // accumulator buffer of this tile
                 const uint32_t acc = tmem_base + ab * C::ACC_COLS;
                 mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);   // the tile two back has been read out of this buffer
+                TRACE(tcount, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     if (!p.presplit) mbar_wait(&split[s], ph);
+                    if (kb == 0) TRACE(tcount, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t d_ahi = umma_desc(st + A_RAW), d_alo = umma_desc(st + A_RAW + A_H);
@@ -224,12 +249,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int k = 0; k < TK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
                         umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                        umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                        umma_f16(acc + TN, d_ahi + adv, d_wlo + adv, IDESC, 1u);
+                        umma_f16(acc + CORR, d_alo + adv, d_whi + adv, IDESC, MERGED ? 1u : (uint32_t)((kb | k) != 0));
+                        umma_f16(acc + CORR, d_ahi + adv, d_wlo + adv, IDESC, 1u);
                     }
                     umma_commit(&empty[s]);
                 }
                 umma_commit(&acc_full[ab]);
+                TRACE(tcount, 3);
             }
         }
     } else if (warp < 10) {
@@ -275,8 +301,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int row = pidx >> 3;
                     const int k0 = ((pidx & 7) ^ (row & 7)) << 2;     // logical k of the slot (Swizzle<3,4,3>)
                     uint2 h, l;
-                    split2(v[i].x * sc[i], v[i].y * sc[i], h.x, l.x);
-                    split2(v[i].z * sc[i], v[i].w * sc[i], h.y, l.y);
+                    split2<MERGED>(v[i].x * sc[i], v[i].y * sc[i], h.x, l.x);
+                    split2<MERGED>(v[i].z * sc[i], v[i].w * sc[i], h.y, l.y);
                     // fp16 tile: 64-byte rows, 16-byte chunk index XOR (row/2)%4 (Swizzle<2,4,3>)
                     const int off = row * 64 + ((((k0 >> 3) ^ (row >> 1)) & 3) << 4) + ((k0 & 7) << 1);
                     *reinterpret_cast<uint2*>(hi + off) = h;
@@ -284,6 +310,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
                 mbar_arrive(&split[s]);
+#ifdef MI_TC_TRACE
+                if (t == 0 && kb == 0) TRACE((tile - (int)blockIdx.x) / (int)gridDim.x, 13);
+#endif
             }
         }
     } else {
@@ -307,6 +336,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             const float rowsc = e.alpha * __uint_as_float((uint32_t)(127 + e8) << 23);   // alpha * 2^e
             mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
+            if (threadIdx.x == 320) TRACE(tcount, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int i1 = 0, i2 = 0, i3 = 0;
             if (EPI & 1) {
@@ -334,6 +364,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
+                if (!MERGED) {
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -342,8 +373,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
                       "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
                       "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
-                    : "r"(taddr + (uint32_t)TN));
+                    : "r"(taddr + CORR));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = 0u;
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (threadIdx.x == 320 && cc < 4) TRACE(tcount, 5 + cc);
                 if (cc == CH - 1) {                      // all of this warp's TMEM reads are done: release the accumulators
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[ab]);
@@ -356,6 +392,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         rowsc * fmaf(__uint_as_float(w[j]), LO_UNSCALE, __uint_as_float(v[j])),
                         rowsc * fmaf(__uint_as_float(w[j + 1]), LO_UNSCALE, __uint_as_float(v[j + 1])));
                 __syncwarp();
+                if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 16);
                 const int col4 = (lane & 7) * 4;
                 const int n = nb + col4;
                 if (p.c_vec && nb + 32 <= p.N) {
@@ -384,6 +421,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             if (ok && e.resid) gr[u] = __ldg(reinterpret_cast<const float4*>(e.resid + (long long)m * e.resid_ld + n));
                         }
+                        if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 17 + 2 * hb);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int rr = (hb * 4 + u) * 4 + (lane >> 3);
@@ -402,9 +440,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 for (int v4 = 0; v4 < 4; ++v4) x[v4] = silu_fast(x[v4]);
                             }
                             x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w;
+#ifndef MI_TC_NOSTORE
                             *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
+#else
+                            if (x[0] == 1.2345f) p.C[0] = x[1] + x[2] + x[3];
+#endif
                             rowmax[hb * 4 + u] = fmaxf(rowmax[hb * 4 + u], fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
                         }
+                        if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 18 + 2 * hb);
                     }
                 } else {
                     // ---- generic path (ragged N or unaligned rows): scalar, bounds-checked
@@ -441,6 +484,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                 }
                 __syncwarp();
+                if (threadIdx.x == 320 && cc < 4) TRACE(tcount, 9 + cc);
             }
             if (e.amax_out) {                                    // one atomic per row per warp: max over the 8 lanes sharing a row
 #pragma unroll
@@ -457,19 +501,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) TRACE(0, 15);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
-__global__ void f16_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
+__global__ void f16_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, long long n,
+                                 float scale, float lo_scale) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float x = w[i];
+    float x = w[i] * scale;
     __half h = __float2half_rn(x);
     hi[i] = h;
-    lo[i] = __float2half_rn((x - __half2float(h)) * LO_SCALE);
+    lo[i] = __float2half_rn((x - __half2float(h)) * lo_scale);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -506,10 +552,10 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 }
 
 
-template <int STAGES, int TN, int EPI>
+template <int STAGES, int TN, int EPI, int MERGED>
 int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi, const void* W_lo, int ldw,
               cudaStream_t s, const TcParams& p) {
-    using C = Cfg<STAGES, TN>;
+    using C = Cfg<STAGES, TN, MERGED>;
     static bool attr = false;
     int rc;
     CUtensorMap mA, mAl, mWh, mWl;
@@ -518,7 +564,7 @@ int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, con
     if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, true)) != MI_OK) return rc;
     if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, true)) != MI_OK) return rc;
     if (!attr) {
-        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<STAGES, TN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<STAGES, TN, EPI, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
     static int sms = 0;
@@ -529,23 +575,31 @@ int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, con
     }
     const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM);
     const int grid = (int)(tiles < sms ? tiles : sms);        // persistent: one CTA per SM
-    tc_gemm_kernel<STAGES, TN, EPI><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
+    tc_gemm_kernel<STAGES, TN, EPI, MERGED><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
 
 }  // namespace
 
-extern "C" int mi_f16_split(const float* w, void* hi, void* lo, long long n, mi_stream_t stream) {
+#ifdef MI_TC_TRACE
+extern "C" int mi_tc_trace_read(long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * (size_t)n);
+}
+#endif
+
+extern "C" int mi_f16_split(const float* w, void* hi, void* lo, long long n, float scale, float lo_scale, mi_stream_t stream) {
     if (n <= 0) return MI_OK;
     MI_CHECK_ARG(w && hi && lo, "null pointer");
-    f16_split_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)hi, (__half*)lo, n);
+    f16_split_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)hi, (__half*)lo, n, scale, lo_scale);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
 
 static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi, const void* W_lo,
-                        int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
+                        int ldw, float* C, int ldc, const mi_epilogue_t* epi, int flags, mi_stream_t stream) {
+    const bool merged = (flags & MI_TC_MERGED) != 0;
     MI_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "bad dimension");
     if (M == 0 || N == 0) return MI_OK;
     MI_CHECK_ARG(A && W_hi && W_lo && C, "null operand");
@@ -576,6 +630,7 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     p.c_vec = cv;
     p.presplit = A_lo != nullptr;
     if (p.presplit) MI_CHECK_ARG(p.e.a_amax == nullptr, "pre-split A carries no row rescaling");
+    if (merged) MI_CHECK_ARG(p.presplit || p.e.a_amax != nullptr, "the merged format needs the row maxima of A (epi->a_amax)");
     // Column-tile width: 128 (two double-buffered {main, correction} accumulator pairs fill the 512 TMEM columns);
     // 64 only for narrow outputs.
     int tn = (N <= 64) ? 64 : 128;
@@ -583,25 +638,27 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     if (force) tn = atoi(force) <= 64 ? 64 : 128;
     cudaStream_t s = (cudaStream_t)stream;
     const int epi_mode = ((p.e.g1 || p.e.g2 || p.e.g3) ? 1 : 0) | (p.e.z_out ? 2 : 0);
-#define MI_TC_CASE(ST, TNV)                                                                              \
-    switch (epi_mode) {                                                                                     \
-        case 0: return launch_tc<ST, TNV, 0>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
-        case 1: return launch_tc<ST, TNV, 1>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
-        case 2: return launch_tc<ST, TNV, 2>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                    \
-        default: return launch_tc<ST, TNV, 3>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);                   \
+#define MI_TC_CASE(ST, TNV, MG)                                                                          \
+    switch (epi_mode) {                                                                                  \
+        case 0: return launch_tc<ST, TNV, 0, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
+        case 1: return launch_tc<ST, TNV, 1, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
+        case 2: return launch_tc<ST, TNV, 2, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
+        default: return launch_tc<ST, TNV, 3, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);         \
     }
-    if (tn == 128) { MI_TC_CASE(4, 128) }
-    MI_TC_CASE(4, 64)
+    if (merged) { MI_TC_CASE(3, 256, 1) }
+    if (tn == 128) { MI_TC_CASE(4, 128, 0) }
+    MI_TC_CASE(4, 64, 0)
 #undef MI_TC_CASE
 }
 
 extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
-                          float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
-    return tc_gemm_impl(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, C, ldc, epi, stream);
+                          float* C, int ldc, const mi_epilogue_t* epi, int flags, mi_stream_t stream) {
+    return tc_gemm_impl(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, C, ldc, epi, flags, stream);
 }
 
 extern "C" int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
-                                   const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, mi_stream_t stream) {
+                                   const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, int flags,
+                                   mi_stream_t stream) {
     MI_CHECK_ARG(A_lo != nullptr, "null operand");
-    return tc_gemm_impl(M, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, C, ldc, epi, stream);
+    return tc_gemm_impl(M, N, K, A_hi, A_lo, lda, W_hi, W_lo, ldw, C, ldc, epi, flags, stream);
 }

@@ -82,12 +82,25 @@ def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_
     return e
 
 
-def f16_split(w, hi, lo):
-    """hi = fp16(w), lo = fp16((w - hi) * 2^11): operands of the split-precision tensor-core GEMM."""
+TC_MERGED = 1      # MI_TC_MERGED: single-accumulator 128x256 tiles, operands (s x) = hi + lo with unscaled lo
+
+
+def f16_split(w, hi, lo, scale=1.0, lo_scale=2048.0):
+    """hi = fp16(scale w), lo = fp16((scale w - hi) * lo_scale): operands of the split-precision tensor-core GEMM
+    ((1, 2^11): separate-accumulator format; (s, 1): merged format, s a power of two with max |s w| in [2^14, 2^15))."""
     _f32(w)
     if hi.dtype != torch.float16 or lo.dtype != torch.float16:
         raise TypeError("hi/lo must be float16")
-    check(lib().mi_f16_split(_p(w), _p(hi), _p(lo), w.numel(), _stream()), "mi_f16_split")
+    check(lib().mi_f16_split(_p(w), _p(hi), _p(lo), w.numel(), scale, lo_scale, _stream()), "mi_f16_split")
+
+
+def merged_scale(w):
+    """the power of two s with max |s w| in [2^14, 2^15) (1.0 for an all-zero tensor); one host sync"""
+    m = float(w.abs().max())
+    if m == 0.0 or m != m or m == float("inf"):
+        return 1.0
+    import math
+    return 2.0 ** (14 - math.frexp(m)[1] + 1)
 
 
 def tc_ok(A, W):
@@ -97,7 +110,7 @@ def tc_ok(A, W):
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
-            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None):
+            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0):
     """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm."""
     for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
@@ -106,12 +119,12 @@ def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_
     N = W_hi.shape[0] if N is None else N
     e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1, amax_out, a_amax)
     check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
-                           _ld(C_), C.byref(e), _stream()), "mi_tc_gemm")
+                           _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm")
     return C_
 
 
 def tc_gemm_presplit(A_hi, A_lo, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, resid=None,
-                     act=ACT_NONE, alpha=1.0, amax_out=None):
+                     act=ACT_NONE, alpha=1.0, amax_out=None, flags=0):
     """tc_gemm with A given as fp16 (hi, scaled lo) arrays from its producer.  See mi_tc_gemm_presplit."""
     for t in (C_, bias, z_out, resid):
         _f32(t)
@@ -120,7 +133,7 @@ def tc_gemm_presplit(A_hi, A_lo, W_hi, W_lo, C_, M=None, N=None, K=None, bias=No
     N = W_hi.shape[0] if N is None else N
     e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, None)
     check(lib().mi_tc_gemm_presplit(M, N, K, A_hi.data_ptr(), A_lo.data_ptr(), _ld(A_hi), W_hi.data_ptr(), W_lo.data_ptr(),
-                                    _ld(W_hi), C_.data_ptr(), _ld(C_), C.byref(e), _stream()), "mi_tc_gemm_presplit")
+                                    _ld(W_hi), C_.data_ptr(), _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm_presplit")
     return C_
 
 
@@ -131,11 +144,12 @@ def fc_edges(node_off, edge_off, B, N, E, edge_src, edge_dst, edge_graph, seg_pt
                             _p(seg_ptr), _p(dst_ptr), _p(dst_perm), _p(node_graph), _stream()), "mi_fc_edges")
 
 
-def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi, phi_hi=None, phi_lo=None):
+def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi, phi_hi=None, phi_lo=None, op_scale=1.0,
+                 lo_scale=2048.0):
     _f32(x), _f32(phi), _f32(cell_off), _f32(frac_diff), _i32(edge_src), _i32(edge_dst)
     ld = _ld(phi) if phi is not None else _ld(phi_hi)
     check(lib().mi_edge_fourier(_p(x), _p(edge_src), _p(edge_dst), _p(cell_off), E, F, _p(frac_diff), _p(phi),
-                                ld, _p(phi_hi), _p(phi_lo), _stream()), "mi_edge_fourier")
+                                ld, _p(phi_hi), _p(phi_lo), op_scale, lo_scale, _stream()), "mi_edge_fourier")
 
 
 def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None):
