@@ -254,6 +254,7 @@ def main():
     ws = m.decoder.workspace(g, False)
     W = m.decoder.w
     dec = m.decoder
+    presplit, merged = dec.edge_mode(g.E)
     torch.cuda.synchronize()
     evs = []
     for rep in range(3):
@@ -261,14 +262,9 @@ def main():
             q = "l%d." % i
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
-                        act=ops.ACT_SILU, amax_out=ws.amax_a1[i])
-            if dec.use_tc:
-                ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, dec._hi[q + "w_f"], dec._lo[q + "w_f"], ws.a1[0], M=g.E, **epi1)
-            else:
-                dec._linear(ws.phi, q + "w_f", ws.a1[0], g.E, **epi1)
+            dec.edge_gemm1(i, ws, g, g.E, ws.a1[0], False, presplit, merged)
             e1.record()
-            dec._linear(ws.a1[0], q + "w2", ws.a2, g.E, bias=W(q + "b2"), act=ops.ACT_SILU, a_amax=ws.amax_a1[i])
+            dec.edge_gemm2(i, ws, g.E, ws.a1[0], False, merged)
             e2.record()
             evs.append((e0, e1, e2))
     torch.cuda.synchronize()

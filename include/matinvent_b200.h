@@ -64,6 +64,9 @@ typedef struct {
     const float* a_amax;  /* optional [M], mi_tc_gemm only: row-wise max |A[m][:]| from the producer of A; rows
                              are rescaled by a power of two into fp16 range before the split (exact) and the
                              result rows scaled back, so the tensor-core path keeps fp32 dynamic range */
+    const float* col_scale; /* optional [N], mi_tc_gemm only: the accumulator column n is multiplied by col_scale[n]
+                             (together with alpha) before bias / gathers: undoes the per-row power-of-two scales
+                             mi_f16_split_rows applied to W (mi_sgemm rejects it) */
 } mi_epilogue_t;
 
 int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
@@ -80,14 +83,18 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
  *                 correction accumulator (lowest rounding error).  Needs |W| < 65504; A rows larger than
  *                 2^15 need epi->a_amax (see mi_epilogue_t).
  *   MI_TC_MERGED  hi = fp16(s x), lo = fp16(s x - hi) with s a power of two that brings max |x| into
- *                 [2^14, 2^15) (per tensor for W — the caller folds 1/s into epi->alpha —, per row for A via
- *                 epi->a_amax, which is then mandatory): all three products go into ONE accumulator, so a
- *                 128x256 tile double-buffers in TMEM; half the operand traffic per flop, about 3x the
+ *                 [2^14, 2^15) (per output row of W: mi_f16_split_rows, undone by epi->col_scale; per row of A
+ *                 via epi->a_amax, which is then mandatory): all three products go into ONE accumulator, so a
+ *                 128x256 tile double-buffers in TMEM; half the operand traffic per flop, about 2.5x the
  *                 (still ~1e-6 relative) rounding error.
  * mi_f16_split(w, hi, lo, n, scale, lo_scale): hi = fp16(scale * w), lo = fp16((scale * w - hi) * lo_scale);
- * (1, 2048) is the format of flags = 0, (s, 1) the merged one. */
+ * (1, 2048) is the format of flags = 0, (s, 1) the merged one with a caller-chosen s (folded into epi->alpha).
+ * mi_f16_split_rows(w [rows, cols] ld, hi, lo (same ld), inv_scale [rows]): merged format with one scale per row,
+ * chosen on the device (no host synchronisation): s_r = 2^(14 - exponent(max_c |w[r][c]|)), inv_scale[r] = 1 / s_r. */
 #define MI_TC_MERGED 1
 int mi_f16_split(const float* w, void* hi, void* lo, long long n, float scale, float lo_scale, mi_stream_t stream);
+int mi_f16_split_rows(const float* w, int rows, int cols, int ld, void* hi, void* lo, float* inv_scale,
+                      mi_stream_t stream);
 int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,
                float* C, int ldc, const mi_epilogue_t* epi, int flags, mi_stream_t stream);
 /* Same, with A already split by its producer into fp16 (hi, lo) arrays of leading dimension lda

@@ -20,7 +20,7 @@ class Epilogue(C.Structure):
                 ("z_in", c_fp), ("zin_ld", C.c_int),
                 ("resid", c_fp), ("resid_ld", C.c_int),
                 ("act", C.c_int), ("alpha", C.c_float), ("beta", C.c_float), ("splitk", C.c_int),
-                ("amax_out", c_fp), ("a_amax", c_fp)]
+                ("amax_out", c_fp), ("a_amax", c_fp), ("col_scale", c_fp)]
 
 
 i, f, d, ll, u64, p = C.c_int, C.c_float, C.c_double, C.c_longlong, C.c_ulonglong, c_fp
@@ -31,6 +31,7 @@ PROTOTYPES = {
     "mi_device_info": [C.POINTER(i), C.POINTER(i), C.POINTER(i)],
     "mi_sgemm": [i, i, i, i, i, p, i, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_f16_split": [p, p, p, ll, f, f, p],
+    "mi_f16_split_rows": [p, i, i, i, p, p, p, p],
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],

@@ -18,9 +18,9 @@
 //   * fused epilogue (bias + up to 3 row gathers + pre-activation store + SiLU + residual), same contract as
 //     mi_sgemm, 8 warps reading TMEM with tcgen05.ld.
 //
-// Persistent CTA per SM, 128 x TN output tiles (TN in {128,64}), 14 warps: w0 TMA producer, w1 MMA issuer + TMEM
-// owner, w2..9 operand split, w10..17 epilogue (overlapped with the next tile's main loop: TMEM holds two
-// {main, correction} accumulator pairs).  Stage = A_raw 16K | A_hi 8K | A_lo 8K | W_hi TN*64 | W_lo TN*64, 4 stages.
+// Persistent CTA per SM, 128 x TN output tiles (TN in {256 merged, 128, 64}), 16 warps: w0 TMA producer, w1 MMA issuer
+// + TMEM owner, w2..7 operand split, w8..15 epilogue (overlapped with the next tile's main loop: TMEM holds the
+// accumulators of two tiles).  Shared memory: a raw fp32 A ring and an fp16 operand ring (see Cfg).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -31,27 +31,43 @@
 namespace {
 
 constexpr int TM = 128;                              // CTA tile rows; columns TN in {128, 64} (template)
-constexpr int TC_THREADS = 576;   // w0 TMA, w1 MMA, w2..9 operand split, w10..17 epilogue
+constexpr int TC_THREADS = 512;   // w0 TMA, w1 MMA, w2..7 operand split, w8..15 epilogue; 16 warps leave 128 registers per thread
+constexpr int SPLIT_THREADS = 192;
 constexpr int TK = 32;                               // k-block: 32 elements = 128 B of fp32, 64 B of fp16
 // MERGED = 0: two accumulators per tile (main, 2^11-scaled correction), TN <= 128.
 // MERGED = 1: one accumulator per tile, operands carry an UNSCALED fp16 tail (both operands are pre-scaled by
 //             powers of two into [2^14, 2^15) so the tail stays in fp16's useful range): TN = 256 fits the double
 //             buffer, halving operand bytes and split work per flop at ~2.7x the (still FP32-grade) rounding error,
 //             because three times as many truncating accumulations go into the one accumulator.
-template <int STAGES, int TN, int MERGED = 0>
+// Shared memory holds two rings, so that the HBM latency of A does not sit on the round trip of an MMA operand slot
+// and a pre-split A needs no raw staging at all.  The main loop is bound by shared-memory bandwidth, not by the
+// tensor core (profiles/r1_tc_trace.md): per 32-wide k-block of a 128x256 tile the UMMAs read 72 KB of operands,
+// TMA writes 48 KB and the split warps move 32 KB, 152 KB at 128 B/clk = 1190 cycles against 768 of MMA issue.
+//   raw ring  R x 16 KB : fp32 A tiles as TMA delivers them (SWIZZLE_128B); freed as soon as the split warps read them
+//   op ring   S x OPB   : A_hi 8K | A_lo 8K | W_hi TN*64 | W_lo TN*64 (fp16, SWIZZLE_64B); freed by tcgen05.commit
+// PRESPLIT (A arrives as fp16 hi/lo from its producer): no raw ring, deeper op ring.
+template <int TN, int MERGED, int PRESPLIT>
 struct Cfg {
-    static constexpr int A_RAW = TM * TK * 4;                     // 16 KB fp32 tile (TMA, SWIZZLE_128B)
-    static constexpr int A_H = TM * TK * 2;                       // 8 KB fp16 tile (SWIZZLE_64B), x2 (hi, lo)
-    static constexpr int W_H = TN * TK * 2;                       // fp16 weight tile (TMA, SWIZZLE_64B), x2
-    static constexpr int STAGE_BYTES = A_RAW + 2 * A_H + 2 * W_H;
+    static constexpr int A_RAW = TM * TK * 4;                     // 16 KB fp32 tile
+    static constexpr int A_H = TM * TK * 2;                       // 8 KB fp16 tile, x2 (hi, lo)
+    static constexpr int W_H = TN * TK * 2;                       // fp16 weight tile, x2
+    static constexpr int OPB = 2 * A_H + 2 * W_H;                 // one op-ring slot
+    static constexpr int RING_BUDGET = 192 * 1024;
+    static constexpr int R = PRESPLIT ? 0 : (TN == 256 ? 3 : 4);
+    static constexpr int S_FIT = (RING_BUDGET - R * A_RAW) / OPB;
+    static constexpr int S = S_FIT > 6 ? 6 : S_FIT;
+    static constexpr int RAW_BYTES = R * A_RAW, OP_BYTES = S * OPB;
     static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
     static constexpr int EBUF_BYTES = 8 * 32 * EPITCH * 4;        // per-warp transpose buffers of the epilogue
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EBUF_BYTES + 128 /*barriers*/ + 128 /*row exponents*/;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = RAW_BYTES + OP_BYTES + EBUF_BYTES + BAR_BYTES + 128 /*row exponents*/;
     static constexpr uint32_t ACC_COLS = MERGED ? TN : 2 * TN;    // accumulator columns of one tile
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;           // double buffered: tile t+1 accumulates while t drains
     // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (bits 7-9, 10-12 = 0),
     // both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
     static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    static_assert(S >= 2 && SMEM_BYTES <= 232448 && TMEM_COLS <= 512, "configuration does not fit the SM");
+    static_assert((3 * S + 2 * R + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
 
@@ -111,6 +127,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 // SiLU with ex2/rcp approximations (~3e-7 relative, below the GEMM's own error): 5 instructions instead of ~25,
 // the epilogue is issue/latency bound otherwise.
+// 16-byte read-only load that does not allocate in L1: the gathered rows are 4 KB apart (they thrash the L1 sets) and
+// every value is used once per CTA; reuse between CTAs is served by L2.
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // x -> (fp16(x), fp16((x - fp16(x)) * 2^11)) packed for two consecutive elements
 template <int MERGED>
@@ -144,40 +167,68 @@ struct TcParams {
     int presplit; // A is given as two fp16 arrays (hi, scaled lo): TMA loads them straight into the operand tiles
 };
 
-// EPI bit 0: row gathers present, bit 1: pre-activation store (training).  bias / SiLU / residual stay runtime flags.
-template <int STAGES, int TN, int EPI, int MERGED>
+// tcgen05.ld of a 32-lane x 32-column fp32 block (lane = row, registers = consecutive columns); completion is
+// only guaranteed after tcgen05.wait::ld.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+// EPI bit 0: row gathers g1 / g2 present, bit 1: pre-activation store (training), bit 2: third gather g3 and / or
+// residual present.  Compile-time so that the epilogue of the hot instantiations keeps every load of a batch in
+// flight (with all four operand sets live the register allocator serialised the gathers: 15k cycles per 32x32 chunk).
+// bias / SiLU / column scales stay runtime flags.
+template <int TN, int EPI, int MERGED, int PRESPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so the CTAs that share an A row
-    // block run at the same time and hit it in L2).  Pipeline counters run across tiles, so the producer already
-    // streams the next tile's first stages while this tile's epilogue drains TMEM.
-    using C = Cfg<STAGES, TN, MERGED>;
+    // block run at the same time and hit it in L2).  All pipeline counters run across tiles (one flat k-block index
+    // per CTA), so the rings already stream the next tile while this tile's epilogue drains TMEM.
+    using C = Cfg<TN, MERGED, PRESPLIT>;
     constexpr uint32_t TMEM_COLS = C::TMEM_COLS, IDESC = C::IDESC;
     constexpr uint32_t CORR = MERGED ? 0 : TN;            // column offset of the correction accumulator
-    constexpr int A_RAW = C::A_RAW, A_H = C::A_H, W_H = C::W_H, STAGE_BYTES = C::STAGE_BYTES;
+    constexpr int A_RAW = C::A_RAW, A_H = C::A_H, W_H = C::W_H, OPB = C::OPB, S = C::S, R = C::R;
+    constexpr int RR = R > 0 ? R : 1;                     // divisor only
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
-    float* ebuf_all = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);          // 8 warps x 32 x 36 floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::EBUF_BYTES);
-    uint64_t* full = bars;                 // [STAGES] TMA landed
-    uint64_t* split = bars + STAGES;       // [STAGES] fp16 A tiles ready
-    uint64_t* empty = bars + 2 * STAGES;   // [STAGES] MMAs done with the stage
-    uint64_t* acc_full = bars + 3 * STAGES;        // [2] accumulators of a tile complete
-    uint64_t* acc_empty = bars + 3 * STAGES + 2;   // [2] epilogue has drained the accumulator buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
-    int8_t* rexp = reinterpret_cast<int8_t*>(smem + STAGES * STAGE_BYTES + C::EBUF_BYTES + 128);   // [128] row exponents (split warps only)
+    uint8_t* raw_ring = smem;
+    uint8_t* op_ring = smem + C::RAW_BYTES;
+    float* ebuf_all = reinterpret_cast<float*>(smem + C::RAW_BYTES + C::OP_BYTES);      // 8 warps x 32 x EPITCH floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RAW_BYTES + C::OP_BYTES + C::EBUF_BYTES);
+    uint64_t* w_full = bars;                       // [S] TMA landed in the op slot (W, and A hi/lo when PRESPLIT)
+    uint64_t* a_ready = bars + S;                  // [S] split warps have written A hi/lo
+    uint64_t* op_empty = bars + 2 * S;             // [S] MMAs done with the slot
+    uint64_t* raw_full = bars + 3 * S;             // [R] fp32 A tile landed
+    uint64_t* raw_empty = bars + 3 * S + R;        // [R] split warps have consumed it
+    uint64_t* acc_full = bars + 3 * S + 2 * R;     // [2] accumulators of a tile complete
+    uint64_t* acc_empty = acc_full + 2;            // [2] epilogue has drained the accumulator buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+    int8_t* rexp = reinterpret_cast<int8_t*>(smem + C::RAW_BYTES + C::OP_BYTES + C::EBUF_BYTES + C::BAR_BYTES);   // [128] row exponents
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + TK - 1) / TK;
     const int tiles_n = (p.N + TN - 1) / TN;
     const int num_tiles = tiles_n * ((p.M + TM - 1) / TM);
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)nkb;        // k-blocks this CTA goes through
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&split[s], 256);
-            mbar_init(&empty[s], 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&w_full[s], 1);
+            mbar_init(&a_ready[s], SPLIT_THREADS);
+            mbar_init(&op_empty[s], 1);
+        }
+        for (int r = 0; r < R; ++r) {
+            mbar_init(&raw_full[r], 1);
+            mbar_init(&raw_empty[r], SPLIT_THREADS);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -202,49 +253,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+        // One thread feeds both rings: W (and pre-split A) for k-block i as soon as its op slot is free, raw A for
+        // k-block i + R - 1 as soon as the split warps have released that raw slot — raw tiles run ahead of the
+        // op ring, which is what hides the HBM latency of A.
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
             TRACE(0, 14);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+            auto issue_raw = [&](uint32_t idx) {
+                const int tl = (int)(idx / (uint32_t)nkb), kb = (int)(idx % (uint32_t)nkb);
+                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+                const int m0 = (tile / tiles_n) * TM;
+                const int r = (int)(idx % (uint32_t)RR);
+                mbar_wait(&raw_empty[r], ((idx / (uint32_t)RR) & 1) ^ 1);
+                mbar_expect_tx(&raw_full[r], A_RAW);
+                tma_load_2d(raw_ring + r * A_RAW, &mapA, &raw_full[r], kb * TK, m0);
+            };
+            uint32_t a_it = 0;
+            if (!PRESPLIT)
+                for (; a_it + 1 < (uint32_t)R && a_it < total; ++a_it) issue_raw(a_it);
+            for (uint32_t it = 0; it < total; ++it) {
+                const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
+                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
                 const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    if (kb == 0) TRACE(tcount, 0);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full[s], (p.presplit ? 2 * A_H : A_RAW) + 2 * W_H);
-                    if (p.presplit) {
-                        tma_load_2d(st + A_RAW, &mapA, &full[s], kb * TK, m0);
-                        tma_load_2d(st + A_RAW + A_H, &mapAlo, &full[s], kb * TK, m0);
-                    } else {
-                        tma_load_2d(st, &mapA, &full[s], kb * TK, m0);
-                    }
-                    tma_load_2d(st + A_RAW + 2 * A_H, &mapWhi, &full[s], kb * TK, n0);
-                    tma_load_2d(st + A_RAW + 2 * A_H + W_H, &mapWlo, &full[s], kb * TK, n0);
+                const int s = (int)(it % (uint32_t)S);
+                mbar_wait(&op_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+                if (kb == 0) TRACE(tl, 0);
+                uint8_t* st = op_ring + s * OPB;
+                mbar_expect_tx(&w_full[s], (PRESPLIT ? 2 * A_H : 0) + 2 * W_H);
+                if (PRESPLIT) {
+                    tma_load_2d(st, &mapA, &w_full[s], kb * TK, m0);
+                    tma_load_2d(st + A_H, &mapAlo, &w_full[s], kb * TK, m0);
                 }
+                tma_load_2d(st + 2 * A_H, &mapWhi, &w_full[s], kb * TK, n0);
+                tma_load_2d(st + 2 * A_H + W_H, &mapWlo, &w_full[s], kb * TK, n0);
+                if (!PRESPLIT && a_it < total) issue_raw(a_it++);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-                const uint32_t ab = tcount & 1;                  // accumulator buffer of this tile
+            uint32_t it = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const uint32_t ab = (uint32_t)tl & 1;            // accumulator buffer of this tile
                 const uint32_t acc = tmem_base + ab * C::ACC_COLS;
-                mbar_wait(&acc_empty[ab], ((tcount >> 1) & 1) ^ 1);   // the tile two back has been read out of this buffer
-                TRACE(tcount, 1);
+                mbar_wait(&acc_empty[ab], (((uint32_t)tl >> 1) & 1) ^ 1);   // the tile two back has been read out of this buffer
+                TRACE(tl, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
-                    if (!p.presplit) mbar_wait(&split[s], ph);
-                    if (kb == 0) TRACE(tcount, 2);
+                    const int s = (int)(it % (uint32_t)S);
+                    const uint32_t ph = (it / (uint32_t)S) & 1;
+                    mbar_wait(&w_full[s], ph);
+                    if (!PRESPLIT) mbar_wait(&a_ready[s], ph);
+                    if (kb == 0) TRACE(tl, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t d_ahi = umma_desc(st + A_RAW), d_alo = umma_desc(st + A_RAW + A_H);
-                    const uint64_t d_whi = umma_desc(st + A_RAW + 2 * A_H), d_wlo = umma_desc(st + A_RAW + 2 * A_H + W_H);
+                    const uint32_t st = smem_u32(op_ring + s * OPB);
+                    const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + A_H);
+                    const uint64_t d_whi = umma_desc(st + 2 * A_H), d_wlo = umma_desc(st + 2 * A_H + W_H);
 #pragma unroll
                     for (int k = 0; k < TK / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
@@ -252,18 +315,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         umma_f16(acc + CORR, d_alo + adv, d_whi + adv, IDESC, MERGED ? 1u : (uint32_t)((kb | k) != 0));
                         umma_f16(acc + CORR, d_ahi + adv, d_wlo + adv, IDESC, 1u);
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&op_empty[s]);
                 }
                 umma_commit(&acc_full[ab]);
-                TRACE(tcount, 3);
+                TRACE(tl, 3);
             }
         }
-    } else if (warp < 10) {
-        // ===================== operand split warps (w2..9) =====================
-        const int t = threadIdx.x - 64;     // 0..255
+    } else if (warp < 8) {
+        // ===================== operand split warps (w2..7) =====================
+        const int t = threadIdx.x - 64;     // 0..191
         const mi_epilogue_t& e = p.e;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles && !p.presplit; tile += gridDim.x) {
+        for (int tl = 0; tl < my_tiles && !PRESPLIT; ++tl) {
+            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int m0 = (tile / tiles_n) * TM;
             // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
             // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
@@ -275,29 +339,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int ex = (int)((__float_as_uint(__ldg(e.a_amax + m)) >> 23) & 0xff) - 127;
                     e8 = max(-100, min(ex - 14, 100));
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");      // everyone is done reading the previous tile's exponents
+                asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory");      // everyone is done reading the previous tile's exponents
                 if (t < TM) rexp[t] = (int8_t)e8;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(SPLIT_THREADS) : "memory");
             }
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                const float4* raw = reinterpret_cast<const float4*>(smem + s * STAGE_BYTES);
-                uint8_t* hi = smem + s * STAGE_BYTES + A_RAW;
+                const int r = (int)(it % (uint32_t)RR), s = (int)(it % (uint32_t)S);
+                mbar_wait(&raw_full[r], (it / (uint32_t)RR) & 1);
+                const float4* raw = reinterpret_cast<const float4*>(raw_ring + r * A_RAW);
+                uint8_t* hi = op_ring + s * OPB;
                 uint8_t* lo = hi + A_H;
                 // all loads first (the stores below may alias them as far as the compiler knows), then convert + store
-                float4 v[4];
-                float sc[4];
+                constexpr int NV = (TM * TK / 4 + SPLIT_THREADS - 1) / SPLIT_THREADS;   // 1024 float4 over 192 threads: 6, last one partial
+                float4 v[NV];
+                float sc[NV];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {                         // 4 float4 per thread
-                    const int pidx = i * 256 + t;                     // physical float4 slot in the 128B-swizzled fp32 tile
-                    v[i] = raw[pidx];
-                    sc[i] = __uint_as_float((uint32_t)(127 - (int)rexp[pidx >> 3]) << 23);      // 2^-e, exact
+                for (int i = 0; i < NV; ++i) {
+                    const int pidx = i * SPLIT_THREADS + t;           // physical float4 slot in the 128B-swizzled fp32 tile
+                    if (pidx < TM * TK / 4) {
+                        v[i] = raw[pidx];
+                        sc[i] = __uint_as_float((uint32_t)(127 - (int)rexp[pidx >> 3]) << 23);      // 2^-e, exact
+                    }
                 }
+                mbar_wait(&op_empty[s], ((it / (uint32_t)S) & 1) ^ 1);   // MMAs of the slot's previous use are done
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int pidx = i * 256 + t;
+                for (int i = 0; i < NV; ++i) {
+                    const int pidx = i * SPLIT_THREADS + t;
+                    if (pidx >= TM * TK / 4) break;
                     const int row = pidx >> 3;
                     const int k0 = ((pidx & 7) ^ (row & 7)) << 2;     // logical k of the slot (Swizzle<3,4,3>)
                     uint2 h, l;
@@ -308,24 +376,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     *reinterpret_cast<uint2*>(hi + off) = h;
                     *reinterpret_cast<uint2*>(lo + off) = l;
                 }
+                // Release the raw slot only now: the stores above consumed every loaded register, so the LDS results
+                // have landed.  (An arrive issued right behind the LDS instructions overtook them, and TMA refilled
+                // the slot under the loads now and then.)
+                mbar_arrive(&raw_empty[r]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(&split[s]);
+                mbar_arrive(&a_ready[s]);
 #ifdef MI_TC_TRACE
-                if (t == 0 && kb == 0) TRACE((tile - (int)blockIdx.x) / (int)gridDim.x, 13);
+                if (t == 0 && kb == 0) TRACE(tl, 13);
 #endif
             }
         }
     } else {
-        // ===================== epilogue warps (w10..17), overlapped with the next tile's main loop =====================
+        // ===================== epilogue warps (w8..15), overlapped with the next tile's main loop =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int hf = (warp - 10) >> 2;             // column half handled by this warp
+        const int hf = (warp - 8) >> 2;              // column half handled by this warp
         constexpr int EP = C::EPITCH;
-        float* ebuf = ebuf_all + (warp - 10) * (32 * EP);
+        float* ebuf = ebuf_all + (warp - 8) * (32 * EP);
         const mi_epilogue_t& e = p.e;
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        constexpr int CH = TN / 64;                  // 32-column chunks per warp
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
-            const uint32_t ab = tcount & 1;
+            const uint32_t ab = (uint32_t)tl & 1;
             const uint32_t acc = tmem_base + ab * C::ACC_COLS;
             // ---- epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global traffic
             const int mrow = m0 + q * 32 + lane;                 // the row this lane owns in TMEM
@@ -335,75 +408,84 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 e8 = max(-100, min(ex - 14, 100));
             }
             const float rowsc = e.alpha * __uint_as_float((uint32_t)(127 + e8) << 23);   // alpha * 2^e
-            mbar_wait(&acc_full[ab], (tcount >> 1) & 1);
-            if (threadIdx.x == 320) TRACE(tcount, 4);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int i1 = 0, i2 = 0, i3 = 0;
             if (EPI & 1) {
                 const bool mrow_ok = mrow < p.M;
                 i1 = (mrow_ok && e.g1) ? (e.g1_idx ? __ldg(e.g1_idx + mrow) : mrow) : 0;
                 i2 = (mrow_ok && e.g2) ? (e.g2_idx ? __ldg(e.g2_idx + mrow) : mrow) : 0;
+            }
+            if (EPI & 4) {
+                const bool mrow_ok = mrow < p.M;
                 i3 = (mrow_ok && e.g3) ? (e.g3_idx ? __ldg(e.g3_idx + mrow) : mrow) : 0;
             }
-            constexpr int CH = TN / 64;                          // 32-column chunks per warp
             float rowmax[8];                                     // running max |C| of the 8 rows this lane touches
 #pragma unroll
             for (int u = 0; u < 8; ++u) rowmax[u] = 0.f;
+            mbar_wait(&acc_full[ab], ((uint32_t)tl >> 1) & 1);
+            if (threadIdx.x == 320) TRACE(tl, 4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // Next chunk's TMEM read in flight while this one is written out — only where the registers allow it
+            // (one accumulator, no gather operands).
+            constexpr bool PREFETCH = MERGED && !(EPI & 1);
+            uint32_t v[32], w[32];
+            const uint32_t tbase = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * CH * 32);
+            if (PREFETCH) tmem_ld32(tbase, v);
 #pragma unroll 1
             for (int cc = 0; cc < CH; ++cc) {
-                const int c = hf * CH + cc;
-                const int nb = n0 + c * 32;
-                uint32_t v[32], w[32];
-                const uint32_t taddr = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                if (!MERGED) {
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
-                      "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
-                      "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
-                      "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
-                    : "r"(taddr + CORR));
-                } else {
+                const int nb = n0 + (hf * CH + cc) * 32;
+                const int col4 = (lane & 7) * 4;
+                const int n = nb + col4;
+                const bool live = nb < p.N;              // warp-uniform
+                const bool fast = live && p.c_vec && nb + 32 <= p.N;
+                // Row gathers g1 / g2 of the chunk: 2 x 4 x 16-byte loads per lane and half chunk, issued so that their
+                // L2 round trips hide behind the TMEM read + transpose (first half) and behind the first half's
+                // arithmetic (second half).  Rows past M read row index 0 and are dropped at the store.
+                float4 ga0[4], gb0[4], ga1[4], gb1[4];
+                auto issue_gathers = [&](int hb, float4 (&ga)[4], float4 (&gb)[4]) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = 0u;
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = (hb * 4 + u) * 4 + (lane >> 3);
+                        const int r1 = __shfl_sync(0xffffffffu, i1, rr), r2 = __shfl_sync(0xffffffffu, i2, rr);
+                        ga[u] = gb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (e.g1) ga[u] = ldg_stream4(e.g1 + (long long)r1 * e.g1_ld + n);
+                        if (e.g2) gb[u] = ldg_stream4(e.g2 + (long long)r2 * e.g2_ld + n);
+                    }
+                };
+                if (!PREFETCH) {
+                    tmem_ld32(tbase + (uint32_t)(cc * 32), v);
+                    if (!MERGED) tmem_ld32(tbase + (uint32_t)(cc * 32) + CORR, w);
                 }
+                if ((EPI & 1) && fast) issue_gathers(0, ga0, gb0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (threadIdx.x == 320 && cc < 4) TRACE(tcount, 5 + cc);
+                if (threadIdx.x == 320 && cc < 4) TRACE(tl, 5 + cc);
                 if (cc == CH - 1) {                      // all of this warp's TMEM reads are done: release the accumulators
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&acc_empty[ab]);
                 }
-                if (nb >= p.N) continue;                 // warp-uniform
+                if (live) {
 #pragma unroll
-#pragma unroll
-                for (int j = 0; j < 32; j += 2)          // STS.64, bank = (2*lane + j) % 32: conflict-free
-                    *reinterpret_cast<float2*>(ebuf + lane * EP + j) = make_float2(
-                        rowsc * fmaf(__uint_as_float(w[j]), LO_UNSCALE, __uint_as_float(v[j])),
-                        rowsc * fmaf(__uint_as_float(w[j + 1]), LO_UNSCALE, __uint_as_float(v[j + 1])));
+                    for (int j = 0; j < 32; j += 2) {        // STS.64, bank = (2*lane + j) % 32: conflict-free
+                        float y0 = __uint_as_float(v[j]), y1 = __uint_as_float(v[j + 1]);
+                        if (!MERGED) {
+                            y0 = fmaf(__uint_as_float(w[j]), LO_UNSCALE, y0);
+                            y1 = fmaf(__uint_as_float(w[j + 1]), LO_UNSCALE, y1);
+                        }
+                        *reinterpret_cast<float2*>(ebuf + lane * EP + j) = make_float2(rowsc * y0, rowsc * y1);
+                    }
+                }
                 __syncwarp();
-                if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 16);
-                const int col4 = (lane & 7) * 4;
-                const int n = nb + col4;
-                if (p.c_vec && nb + 32 <= p.N) {
-                    // ---- fast path: whole chunk in range, 16-byte accesses.  Software-pipelined in two batches of four
-                    // row groups: all gather / residual loads of a batch are issued before any arithmetic or store, so
-                    // their L2 round trips overlap (the compiler will not move loads across the stores by itself).
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (PREFETCH && cc + 1 < CH) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v);
+                if ((EPI & 1) && fast) issue_gathers(1, ga1, gb1);
+                if (threadIdx.x == 320 && cc == 0) TRACE(tl, 16);
+                if (fast) {
+                    // ---- fast path: whole chunk in range, 16-byte accesses, two batches of four row groups
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+                    if (e.col_scale) cs4 = __ldg(reinterpret_cast<const float4*>(e.col_scale + n));
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        float4 ga[4], gb[4], gc[4], gr[4];
+                        float4 gc[4], gr[4];
+                        float2 xa[4], xb[4];
                         int mm[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
@@ -411,35 +493,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const int m = m0 + q * 32 + rr;
                             mm[u] = m;
                             const bool ok = m < p.M;
-                            ga[u] = gb[u] = gc[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (EPI & 1) {
-                                const int r1 = __shfl_sync(0xffffffffu, i1, rr), r2 = __shfl_sync(0xffffffffu, i2, rr),
-                                          r3 = __shfl_sync(0xffffffffu, i3, rr);
-                                if (ok && e.g1) ga[u] = __ldg(reinterpret_cast<const float4*>(e.g1 + (long long)r1 * e.g1_ld + n));
-                                if (ok && e.g2) gb[u] = __ldg(reinterpret_cast<const float4*>(e.g2 + (long long)r2 * e.g2_ld + n));
-                                if (ok && e.g3) gc[u] = __ldg(reinterpret_cast<const float4*>(e.g3 + (long long)r3 * e.g3_ld + n));
+                            gc[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (EPI & 4) {
+                                const int r3 = __shfl_sync(0xffffffffu, i3, rr);
+                                if (ok && e.g3) gc[u] = ldg_stream4(e.g3 + (long long)r3 * e.g3_ld + n);
+                                if (ok && e.resid) gr[u] = ldg_stream4(e.resid + (long long)m * e.resid_ld + n);
                             }
-                            if (ok && e.resid) gr[u] = __ldg(reinterpret_cast<const float4*>(e.resid + (long long)m * e.resid_ld + n));
+                            xa[u] = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4);
+                            xb[u] = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4 + 2);
                         }
-                        if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 17 + 2 * hb);
+                        if (threadIdx.x == 320 && cc == 0) TRACE(tl, 17 + 2 * hb);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const int rr = (hb * 4 + u) * 4 + (lane >> 3);
                             const int m = mm[u];
                             if (m >= p.M) continue;
-                            const float2 xa = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4);
-                            const float2 xb = *reinterpret_cast<const float2*>(ebuf + rr * EP + col4 + 2);
-                            float x[4] = {xa.x + bias4.x, xa.y + bias4.y, xb.x + bias4.z, xb.y + bias4.w};
+                            float x[4] = {fmaf(xa[u].x, cs4.x, bias4.x), fmaf(xa[u].y, cs4.y, bias4.y),
+                                          fmaf(xb[u].x, cs4.z, bias4.z), fmaf(xb[u].y, cs4.w, bias4.w)};
                             if (EPI & 1) {
-                                x[0] += ga[u].x + gb[u].x + gc[u].x; x[1] += ga[u].y + gb[u].y + gc[u].y;
-                                x[2] += ga[u].z + gb[u].z + gc[u].z; x[3] += ga[u].w + gb[u].w + gc[u].w;
+                                const float4 a4 = hb ? ga1[u] : ga0[u], b4 = hb ? gb1[u] : gb0[u];
+                                x[0] += a4.x + b4.x; x[1] += a4.y + b4.y; x[2] += a4.z + b4.z; x[3] += a4.w + b4.w;
                             }
+                            if (EPI & 4) { x[0] += gc[u].x; x[1] += gc[u].y; x[2] += gc[u].z; x[3] += gc[u].w; }
                             if (EPI & 2) *reinterpret_cast<float4*>(e.z_out + (long long)m * e.z_ld + n) = make_float4(x[0], x[1], x[2], x[3]);
                             if (e.act == MI_ACT_SILU) {
 #pragma unroll
                                 for (int v4 = 0; v4 < 4; ++v4) x[v4] = silu_fast(x[v4]);
                             }
-                            x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w;
+                            if (EPI & 4) { x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w; }
 #ifndef MI_TC_NOSTORE
                             *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
 #else
@@ -447,9 +527,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #endif
                             rowmax[hb * 4 + u] = fmaxf(rowmax[hb * 4 + u], fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
                         }
-                        if (threadIdx.x == 320 && cc == 0) TRACE(tcount, 18 + 2 * hb);
+                        if (threadIdx.x == 320 && cc == 0) TRACE(tl, 18 + 2 * hb);
                     }
-                } else {
+                } else if (live) {
                     // ---- generic path (ragged N or unaligned rows): scalar, bounds-checked
 #pragma unroll 1
                     for (int rr0 = 0; rr0 < 32; rr0 += 4) {
@@ -459,32 +539,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (EPI & 1) {
                             r1 = __shfl_sync(0xffffffffu, i1, rr);
                             r2 = __shfl_sync(0xffffffffu, i2, rr);
-                            r3 = __shfl_sync(0xffffffffu, i3, rr);
                         }
+                        if (EPI & 4) r3 = __shfl_sync(0xffffffffu, i3, rr);
                         float rmax = 0.f;
                         if (m < p.M) {
                             float* crow = p.C + (long long)m * p.ldc + n;
                             for (int u = 0; u < 4; ++u) {
                                 if (n + u >= p.N) continue;
                                 float y = ebuf[rr * EP + col4 + u];
+                                if (e.col_scale) y *= __ldg(e.col_scale + n + u);
                                 if (e.bias) y += __ldg(e.bias + n + u);
                                 if (EPI & 1) {
                                     if (e.g1) y += __ldg(e.g1 + (long long)r1 * e.g1_ld + n + u);
                                     if (e.g2) y += __ldg(e.g2 + (long long)r2 * e.g2_ld + n + u);
-                                    if (e.g3) y += __ldg(e.g3 + (long long)r3 * e.g3_ld + n + u);
                                 }
+                                if ((EPI & 4) && e.g3) y += __ldg(e.g3 + (long long)r3 * e.g3_ld + n + u);
                                 if (EPI & 2) e.z_out[(long long)m * e.z_ld + n + u] = y;
                                 if (e.act == MI_ACT_SILU) y = silu_fast(y);
-                                if (e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
+                                if ((EPI & 4) && e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
                                 crow[u] = y;
                                 rmax = fmaxf(rmax, fabsf(y));
                             }
                         }
-                        rowmax[rr0 >> 2] = fmaxf(rowmax[rr0 >> 2], rmax);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)              // static indices keep rowmax[] in registers
+                            if (u == (rr0 >> 2)) rowmax[u] = fmaxf(rowmax[u], rmax);
                     }
                 }
                 __syncwarp();
-                if (threadIdx.x == 320 && cc < 4) TRACE(tcount, 9 + cc);
+                if (threadIdx.x == 320 && cc < 4) TRACE(tl, 9 + cc);
             }
             if (e.amax_out) {                                    // one atomic per row per warp: max over the 8 lanes sharing a row
 #pragma unroll
@@ -516,6 +599,29 @@ __global__ void f16_split_kernel(const float* __restrict__ w, __half* __restrict
     __half h = __float2half_rn(x);
     hi[i] = h;
     lo[i] = __float2half_rn((x - __half2float(h)) * lo_scale);
+}
+
+// one warp per row: power-of-two scale from the row maximum, merged-format split (hi = fp16(s w), lo = fp16(s w - hi))
+__global__ void f16_split_rows_kernel(const float* __restrict__ w, int rows, int cols, int ld, __half* __restrict__ hi,
+                                      __half* __restrict__ lo, float* __restrict__ inv_scale) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* wr = w + (long long)row * ld;
+    float mx = 0.f;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, fabsf(wr[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int ex = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127;         // max in [2^ex, 2^(ex+1))
+    if (mx == 0.f || ex > 100) ex = 14;                               // all-zero (or non-finite) row: scale 1
+    ex = max(ex, -100);
+    const float s = __uint_as_float((uint32_t)(127 + 14 - ex) << 23); // 2^(14 - ex), exact
+    for (int c = lane; c < cols; c += 32) {
+        const float x = wr[c] * s;
+        const __half h = __float2half_rn(x);
+        hi[(long long)row * ld + c] = h;
+        lo[(long long)row * ld + c] = __float2half_rn(x - __half2float(h));
+    }
+    if (lane == 0) inv_scale[row] = __uint_as_float((uint32_t)(127 - 14 + ex) << 23);
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -552,19 +658,19 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 }
 
 
-template <int STAGES, int TN, int EPI, int MERGED>
+template <int TN, int EPI, int MERGED, int PRESPLIT>
 int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi, const void* W_lo, int ldw,
               cudaStream_t s, const TcParams& p) {
-    using C = Cfg<STAGES, TN, MERGED>;
+    using C = Cfg<TN, MERGED, PRESPLIT>;
     static bool attr = false;
     int rc;
     CUtensorMap mA, mAl, mWh, mWl;
-    if ((rc = make_map(&mA, A, M, K, lda, TM, p.presplit != 0)) != MI_OK) return rc;
-    if ((rc = make_map(&mAl, p.presplit ? A_lo : A, M, K, lda, TM, p.presplit != 0)) != MI_OK) return rc;
+    if ((rc = make_map(&mA, A, M, K, lda, TM, PRESPLIT != 0)) != MI_OK) return rc;
+    if ((rc = make_map(&mAl, PRESPLIT ? A_lo : A, M, K, lda, TM, PRESPLIT != 0)) != MI_OK) return rc;
     if ((rc = make_map(&mWh, W_hi, N, K, ldw, TN, true)) != MI_OK) return rc;
     if ((rc = make_map(&mWl, W_lo, N, K, ldw, TN, true)) != MI_OK) return rc;
     if (!attr) {
-        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<STAGES, TN, EPI, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        MI_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TN, EPI, MERGED, PRESPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr = true;
     }
     static int sms = 0;
@@ -575,9 +681,30 @@ int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, con
     }
     const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM);
     const int grid = (int)(tiles < sms ? tiles : sms);        // persistent: one CTA per SM
-    tc_gemm_kernel<STAGES, TN, EPI, MERGED><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
+    tc_gemm_kernel<TN, EPI, MERGED, PRESPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
+}
+
+template <int TN, int MERGED>
+int dispatch_tc(int epi_mode, bool presplit, int M, int N, int K, const void* A, const void* A_lo, int lda, const void* W_hi,
+                const void* W_lo, int ldw, cudaStream_t s, const TcParams& p) {
+#define MI_TC_CASE(E)                                                                                              \
+    case E:                                                                                                        \
+        return presplit ? launch_tc<TN, E, MERGED, 1>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p)                \
+                        : launch_tc<TN, E, MERGED, 0>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
+    switch (epi_mode) {
+        MI_TC_CASE(0)
+        MI_TC_CASE(1)
+        MI_TC_CASE(2)
+        MI_TC_CASE(3)
+        MI_TC_CASE(4)
+        MI_TC_CASE(5)
+        MI_TC_CASE(6)
+        default:
+        MI_TC_CASE(7)
+    }
+#undef MI_TC_CASE
 }
 
 }  // namespace
@@ -593,6 +720,16 @@ extern "C" int mi_f16_split(const float* w, void* hi, void* lo, long long n, flo
     if (n <= 0) return MI_OK;
     MI_CHECK_ARG(w && hi && lo, "null pointer");
     f16_split_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (__half*)hi, (__half*)lo, n, scale, lo_scale);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
+
+extern "C" int mi_f16_split_rows(const float* w, int rows, int cols, int ld, void* hi, void* lo, float* inv_scale,
+                                 mi_stream_t stream) {
+    if (rows <= 0 || cols <= 0) return MI_OK;
+    MI_CHECK_ARG(w && hi && lo && inv_scale, "null pointer");
+    MI_CHECK_ARG(ld >= cols, "leading dimension too small");
+    f16_split_rows_kernel<<<mi_div_up(rows, 8), 256, 0, (cudaStream_t)stream>>>(w, rows, cols, ld, (__half*)hi, (__half*)lo, inv_scale);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -627,6 +764,7 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     if (e.z_out) cv = cv && (e.z_ld % 4 == 0) && mi_host_aligned16(e.z_out);
     if (e.z_in) cv = cv && (e.zin_ld % 4 == 0) && mi_host_aligned16(e.z_in);
     if (e.resid) cv = cv && (e.resid_ld % 4 == 0) && mi_host_aligned16(e.resid);
+    if (e.col_scale) cv = cv && mi_host_aligned16(e.col_scale);
     p.c_vec = cv;
     p.presplit = A_lo != nullptr;
     if (p.presplit) MI_CHECK_ARG(p.e.a_amax == nullptr, "pre-split A carries no row rescaling");
@@ -637,18 +775,10 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     const char* force = getenv("MI_TC_TN");
     if (force) tn = atoi(force) <= 64 ? 64 : 128;
     cudaStream_t s = (cudaStream_t)stream;
-    const int epi_mode = ((p.e.g1 || p.e.g2 || p.e.g3) ? 1 : 0) | (p.e.z_out ? 2 : 0);
-#define MI_TC_CASE(ST, TNV, MG)                                                                          \
-    switch (epi_mode) {                                                                                  \
-        case 0: return launch_tc<ST, TNV, 0, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
-        case 1: return launch_tc<ST, TNV, 1, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
-        case 2: return launch_tc<ST, TNV, 2, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);          \
-        default: return launch_tc<ST, TNV, 3, MG>(M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);         \
-    }
-    if (merged) { MI_TC_CASE(3, 256, 1) }
-    if (tn == 128) { MI_TC_CASE(4, 128, 0) }
-    MI_TC_CASE(4, 64, 0)
-#undef MI_TC_CASE
+    const int epi_mode = ((p.e.g1 || p.e.g2) ? 1 : 0) | (p.e.z_out ? 2 : 0) | ((p.e.g3 || p.e.resid) ? 4 : 0);
+    if (merged) return dispatch_tc<256, 1>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
+    if (tn == 128) return dispatch_tc<128, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
+    return dispatch_tc<64, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
 }
 
 extern "C" int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, const void* W_lo, int ldw,

@@ -13,6 +13,7 @@ under DiffCSPModule / models/suite.  Everything arithmetic runs in the CUDA libr
   * edges are static per batch (graph.py) instead of block_diag + nonzero per forward (:238-242).
 """
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -136,6 +137,10 @@ class CSPNet(nn.Module):
         self.use_tc = True
         self._flat_hi = self._flat_lo = None
         self._hi, self._lo = {}, {}
+        # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
+        # the edge count fills the machine with 256-wide tiles (see forward_graph)
+        self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
+        self._mhi, self._mlo, self._minv = {}, {}, {}
         self._tc_version = None
         self.reset_parameters()
 
@@ -154,6 +159,7 @@ class CSPNet(nn.Module):
         self._rebuild_views()
         self._ws, self._graphs = {}, {}
         self._flat_hi = self._flat_lo = None
+        self._mhi, self._mlo, self._minv = {}, {}, {}
         self._tc_version = None
         return r
 
@@ -174,6 +180,15 @@ class CSPNet(nn.Module):
             self._hi = {k: self._flat_hi[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
             self._lo = {k: self._flat_lo[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
         ops.f16_split(self.flat.data, self._flat_hi, self._flat_lo)
+        if self.use_merged:
+            for i in range(self.num_layers):
+                for k in ("l%d.w_f" % i, "l%d.w2" % i):
+                    w = self._views[k]
+                    if k not in self._mhi:
+                        self._mhi[k] = torch.empty_like(w, dtype=torch.float16)
+                        self._mlo[k] = torch.empty_like(w, dtype=torch.float16)
+                        self._minv[k] = torch.empty(w.shape[0], device=w.device, dtype=torch.float32)
+                    ops.f16_split_rows(w, self._mhi[k], self._mlo[k], self._minv[k])
         self._tc_version = ver
 
     def _linear(self, A, wname, C, M, **epi):
@@ -336,6 +351,40 @@ class CSPNet(nn.Module):
             self._ws[key] = ws
         return ws
 
+    # ------------------------------------------------------------------ per-edge GEMMs (the dominant launches)
+    def edge_mode(self, E):
+        """(presplit, merged): Phi arrives pre-split from mi_edge_fourier when its rows are TMA-legal; the two per-edge
+        GEMMs use 128x256 single-accumulator tiles once they fill every SM (fewer operand bytes per flop; ~2.5x the
+        rounding error of the two-accumulator 128x128 tiles, both FP32-grade)."""
+        H, F = self.hidden_dim, self.num_freqs
+        presplit = self.use_tc and (6 * F) % 8 == 0
+        merged = (presplit and self.use_merged and H % 256 == 0 and
+                  ((E + 127) // 128) * (H // 256) >= ops.sm_count())
+        return presplit, merged
+
+    def edge_gemm1(self, i, ws, g, E, a1, train, presplit, merged):
+        """a1 = silu(Phi W_F^T + P'[src] + Q[dst])   (first edge linear, cspnet.py:59-72, per-edge part)"""
+        H, q = self.hidden_dim, "l%d." % i
+        epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
+                    z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
+        if merged:
+            ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, self._mhi[q + "w_f"], self._mlo[q + "w_f"], a1, M=E,
+                                 alpha=2.0 ** -14, col_scale=self._minv[q + "w_f"], flags=ops.TC_MERGED, **epi1)
+        elif presplit:
+            ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, self._hi[q + "w_f"], self._lo[q + "w_f"], a1, M=E, **epi1)
+        else:
+            self._linear(ws.phi, q + "w_f", a1, E, **epi1)
+
+    def edge_gemm2(self, i, ws, E, a1, train, merged):
+        """a2 = silu(a1 W_2^T + b_2)   (second edge linear, cspnet.py:73-75)"""
+        q = "l%d." % i
+        epi2 = dict(bias=self._views[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU, a_amax=ws.amax_a1[i])
+        if merged:
+            ops.tc_gemm(a1, self._mhi[q + "w2"], self._mlo[q + "w2"], ws.a2, M=E, col_scale=self._minv[q + "w2"],
+                        flags=ops.TC_MERGED, **epi2)
+        else:
+            self._linear(a1, q + "w2", ws.a2, E, **epi2)
+
     # ------------------------------------------------------------------ forward
     def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None):
         """Score network on a prebuilt graph.  temb [B,T], a [N,A], x [N,3], l [B,3,3] fp32 CUDA.
@@ -355,9 +404,10 @@ class CSPNet(nn.Module):
         self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
         self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
         ops.lattice_ip(l, ws.ips, B)
-        presplit = self.use_tc and (6 * F) % 8 == 0
+        presplit, merged = self.edge_mode(E)
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
-                         ws.phi_hi if presplit else None, ws.phi_lo if presplit else None)
+                         ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
+                         op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
         for i in range(L):
             q = "l%d." % i
             k = i if train else 0
@@ -377,14 +427,8 @@ class CSPNet(nn.Module):
             # per-edge GEMM then adds two gathered rows instead of three
             ops.lattice_linear(l, W[q + "w_l"], W[q + "b1"], ws.cb, B, H)
             self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2, g.node_graph)])
-            epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
-                        z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
-            if presplit:
-                ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, self._hi[q + "w_f"], self._lo[q + "w_f"], a1, M=E, **epi1)
-            else:
-                self._linear(ws.phi, q + "w_f", a1, E, **epi1)
-            self._linear(a1, q + "w2", ws.a2, E, bias=W[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU,
-                         a_amax=ws.amax_a1[i])
+            self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
+            self.edge_gemm2(i, ws, E, a1, train, merged)
             # scatter-mean over the source node (cspnet.py:79)
             ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True, amax_out=ws.amax_agg[i])
             # node model + residual (cspnet.py:77-91)

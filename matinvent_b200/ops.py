@@ -63,10 +63,10 @@ def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None
     return C_
 
 
-def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out=None, a_amax=None):
+def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out=None, a_amax=None, col_scale=None):
     e = Epilogue()
-    _f32(amax_out), _f32(a_amax)
-    e.amax_out, e.a_amax = _p(amax_out), _p(a_amax)
+    _f32(amax_out), _f32(a_amax), _f32(col_scale)
+    e.amax_out, e.a_amax, e.col_scale = _p(amax_out), _p(a_amax), _p(col_scale)
     e.bias = _p(bias)
     g = list(gathers) + [(None, None)] * (3 - len(gathers))
     for k, (src, idx) in enumerate(g[:3]):
@@ -82,6 +82,21 @@ def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_
     return e
 
 
+_SM_COUNT = None
+
+
+def sm_count():
+    """SMs of the current device (mi_device_info), cached"""
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        sm, ma, mi = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = lib().mi_device_info(C.byref(sm), C.byref(ma), C.byref(mi))
+        if rc != 0:
+            raise RuntimeError("mi_device_info failed (rc=%d)" % rc)
+        _SM_COUNT = int(sm.value)
+    return _SM_COUNT
+
+
 TC_MERGED = 1      # MI_TC_MERGED: single-accumulator 128x256 tiles, operands (s x) = hi + lo with unscaled lo
 
 
@@ -92,6 +107,16 @@ def f16_split(w, hi, lo, scale=1.0, lo_scale=2048.0):
     if hi.dtype != torch.float16 or lo.dtype != torch.float16:
         raise TypeError("hi/lo must be float16")
     check(lib().mi_f16_split(_p(w), _p(hi), _p(lo), w.numel(), scale, lo_scale, _stream()), "mi_f16_split")
+
+
+def f16_split_rows(w, hi, lo, inv_scale):
+    """merged-format split of a weight matrix [rows, cols] with one power-of-two scale per row, chosen on the device;
+    inv_scale [rows] is what tc_gemm's col_scale takes.  See mi_f16_split_rows."""
+    _f32(w), _f32(inv_scale)
+    if hi.dtype != torch.float16 or lo.dtype != torch.float16 or _ld(hi) != _ld(w) or _ld(lo) != _ld(w):
+        raise TypeError("hi/lo must be float16 with the leading dimension of w")
+    check(lib().mi_f16_split_rows(_p(w), w.shape[0], w.shape[1], _ld(w), _p(hi), _p(lo), _p(inv_scale), _stream()),
+          "mi_f16_split_rows")
 
 
 def merged_scale(w):
@@ -110,28 +135,28 @@ def tc_ok(A, W):
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
-            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0):
+            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0, col_scale=None):
     """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm."""
     for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1, amax_out, a_amax)
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1, amax_out, a_amax, col_scale)
     check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
                            _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm")
     return C_
 
 
 def tc_gemm_presplit(A_hi, A_lo, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, resid=None,
-                     act=ACT_NONE, alpha=1.0, amax_out=None, flags=0):
+                     act=ACT_NONE, alpha=1.0, amax_out=None, flags=0, col_scale=None):
     """tc_gemm with A given as fp16 (hi, scaled lo) arrays from its producer.  See mi_tc_gemm_presplit."""
     for t in (C_, bias, z_out, resid):
         _f32(t)
     M = A_hi.shape[0] if M is None else M
     K = A_hi.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, None)
+    e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, None, col_scale)
     check(lib().mi_tc_gemm_presplit(M, N, K, A_hi.data_ptr(), A_lo.data_ptr(), _ld(A_hi), W_hi.data_ptr(), W_lo.data_ptr(),
                                     _ld(W_hi), C_.data_ptr(), _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm_presplit")
     return C_

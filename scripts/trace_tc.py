@@ -23,10 +23,30 @@ s = ops.merged_scale(W) if merged else 1.0
 ops.f16_split(W, hi, lo, s, 1.0 if merged else 2048.0)
 C = torch.empty(M, N, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(3):
+gemm1 = int(os.environ.get("GEMM1", "0"))      # the first per-edge block: pre-split A, two gathers, row maxima
+if gemm1:
+    Ahi = torch.empty(M, K, device="cuda", dtype=torch.float16)
+    Alo = torch.empty_like(Ahi)
+    Asc = torch.rand(M, K, device="cuda") * 2 - 1
+    ops.f16_split(Asc, Ahi, Alo, 2.0 ** 14 if merged else 1.0, 1.0 if merged else 2048.0)
+    Nn = 2643
+    PQ = torch.randn(Nn, 2 * N, device="cuda")
+    src = torch.randint(0, Nn, (M,), device="cuda").sort().values.int()
+    dst = torch.randint(0, Nn, (M,), device="cuda").int()
+    am = torch.zeros(M, device="cuda")
+evs = []
+for _ in range(5):
     flush.zero_()
-    ops.tc_gemm(A, hi, lo, C, act=act, a_amax=amax, alpha=1.0 / s, flags=merged)
+    evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+    evs[-1][0].record()
+    if gemm1:
+        ops.tc_gemm_presplit(Ahi, Alo, hi, lo, C, gathers=[(PQ[:, :N], src), (PQ[:, N:], dst)], act=act, amax_out=am,
+                             alpha=(2.0 ** -14 if merged else 1.0) / s, flags=merged)
+    else:
+        ops.tc_gemm(A, hi, lo, C, act=act, a_amax=amax, alpha=1.0 / s, flags=merged)
+    evs[-1][1].record()
 torch.cuda.synchronize()
+print("launch times (us):", " ".join("%.1f" % (a.elapsed_time(b) * 1e3) for a, b in evs))
 TT, TS = 8, 24
 buf = (ctypes.c_longlong * (160 * TT * TS))()
 lib = _lib.load()

@@ -106,3 +106,81 @@ def test_tc_gemm_row_rescaling_keeps_fp32_range():
     C2 = torch.empty(M, N, device="cuda")
     ops.tc_gemm(A, hi, lo, C2)
     assert not torch.isfinite(C2).all()          # documents the failure mode the row maxima prevent
+
+
+# ---------------------------------------------------------------- merged single-accumulator format (128x256 tiles)
+def _split_rows(ops, W):
+    hi, lo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=torch.float16)
+    inv = torch.empty(W.shape[0], device="cuda")
+    ops.f16_split_rows(W, hi, lo, inv)
+    return hi, lo, inv
+
+
+def test_f16_split_rows_scales_each_row_into_fp16_range():
+    from matinvent_b200 import ops
+    W = _rand(300, 512, seed=40) * torch.logspace(-8, 6, 300).cuda()[:, None]
+    W[7] = 0.0
+    hi, lo, inv = _split_rows(ops, W)
+    s = 1.0 / inv
+    assert torch.equal(torch.log2(s), torch.log2(s).round())                    # powers of two
+    top = (W * s[:, None]).abs().amax(dim=1)
+    nz = W.abs().amax(dim=1) > 0
+    assert bool(((top[nz] >= 2.0 ** 14) & (top[nz] < 2.0 ** 15)).all()) and float(s[7]) == 1.0
+    rec = (hi.double() + lo.double()) * inv.double()[:, None]
+    row_err = (rec - W.double()).abs().amax(dim=1) / W.abs().amax(dim=1).clamp_min(1e-300).double()
+    assert float(row_err[nz].max()) <= 2.0 ** -21, float(row_err[nz].max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 512, 768), (1, 8, 32), (300, 512, 512), (2643, 1024, 512),
+                                   (257, 100, 512), (34445, 512, 768), (34445, 512, 512), (1000, 512, 1024)])
+def test_tc_gemm_merged_fp32_grade(M, N, K):
+    """merged format: three times as many truncating accumulations in the one accumulator -> looser bound (1e-5)"""
+    from matinvent_b200 import ops
+    A, W = _rand(M, K, seed=1), _rand(N, K, seed=2) * torch.logspace(-3, 3, N).cuda()[:, None]
+    hi, lo, inv = _split_rows(ops, W)
+    amax = A.abs().amax(dim=1).contiguous()
+    C = torch.full((M, N), float("nan"), device="cuda")
+    ops.tc_gemm(A, hi, lo, C, a_amax=amax, col_scale=inv, flags=ops.TC_MERGED)
+    ref = A.double() @ W.double().t()
+    # per output column (W rows differ by 1e6), relative to the largest |a|.|w| of the column: the forward error bound
+    # of a dot product scales with sum |a_k w_k|, not with a possibly cancelled result
+    col_err = (C.double() - ref).abs().amax(dim=0) / (A.double().abs() @ W.double().abs().t()).amax(dim=0)
+    print("merged tc_gemm M=%d N=%d K=%d rel err %.2e" % (M, N, K, float(col_err.max())))
+    assert float(col_err.max()) < 1e-5, float(col_err.max())
+
+
+def test_tc_gemm_merged_needs_row_maxima():
+    from matinvent_b200 import ops
+    from matinvent_b200._lib import MatInventLibError
+    A, W = _rand(64, 64, seed=1), _rand(256, 64, seed=2)
+    hi, lo, inv = _split_rows(ops, W)
+    with pytest.raises(MatInventLibError):
+        ops.tc_gemm(A, hi, lo, torch.empty(64, 256, device="cuda"), col_scale=inv, flags=ops.TC_MERGED)
+
+
+def test_tc_gemm_merged_presplit_fourier_edge_block():
+    """the first per-edge block as CSPNet issues it in merged format: Phi from mi_edge_fourier scaled by 2^14 with an
+    unscaled tail, per-row scaled weight, two gathers, pre-activation store, SiLU, row maxima"""
+    from matinvent_b200 import ops
+    Nn, F, H = 37, 128, 512
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(Nn, 3, generator=g).cuda()
+    E = 5000
+    src = torch.randint(0, Nn, (E,), generator=g).int().cuda()
+    dst = torch.randint(0, Nn, (E,), generator=g).int().cuda()
+    phi = torch.empty(E, 6 * F, device="cuda")
+    phi_hi = torch.empty(E, 6 * F, device="cuda", dtype=torch.float16)
+    phi_lo = torch.empty_like(phi_hi)
+    ops.edge_fourier(x, src, dst, None, E, F, None, phi, phi_hi, phi_lo, op_scale=2.0 ** 14, lo_scale=1.0)
+    assert float(((phi_hi.double() + phi_lo.double()) * 2.0 ** -14 - phi.double()).abs().max()) <= 2.0 ** -22
+    W = _rand(H, 6 * F, seed=4) / (6 * F) ** 0.5
+    hi, lo, inv = _split_rows(ops, W)
+    PQ = _rand(Nn, 2 * H, seed=5)
+    Z, C = torch.empty(E, H, device="cuda"), torch.empty(E, H, device="cuda")
+    amax = torch.zeros(E, device="cuda")
+    ops.tc_gemm_presplit(phi_hi, phi_lo, hi, lo, C, M=E, gathers=[(PQ[:, :H], src), (PQ[:, H:], dst)], z_out=Z,
+                         act=ops.ACT_SILU, alpha=2.0 ** -14, col_scale=inv, amax_out=amax, flags=ops.TC_MERGED)
+    z = phi.double() @ W.double().t() + PQ.double()[src.long(), :H] + PQ.double()[dst.long(), H:]
+    assert rel_err(Z, z) < 5e-6
+    assert rel_err(C, torch.nn.functional.silu(z)) < 5e-6
+    assert torch.equal(amax, C.abs().amax(dim=1))
