@@ -158,8 +158,10 @@ int mi_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const f
  * ips[b] = vec(L_b L_b^T)  (cspnet.py:67-72) */
 int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stream);
 /* out[b][:] = bias + vec(L_b L_b^T) W^T with W [H,9]: the per-crystal term C_b of the split first edge linear
- * (cspnet.py:45,67-72) in one launch */
+ * (cspnet.py:45,67-72).  n_sets weight sets (the layers of the network: the lattices are the same for all of them)
+ * in one launch: set s uses W + s * w_stride, bias + s * bias_stride and writes out + s * out_stride. */
 int mi_lattice_linear(const float* L, const float* W, const float* bias, float* out, int ldo, int B, int H,
+                      int n_sets, long long w_stride, long long bias_stride, long long out_stride,
                       mi_stream_t stream);
 /* out[b] = A[b] (3x3) @ L[b] (3x3)   (cspnet.py:288-289); transL != 0 -> A[b] @ L[b]^T (its backward) */
 int mi_bmm3(const float* A, const float* L, float* out, int B, int transL, mi_stream_t stream);

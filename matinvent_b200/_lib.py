@@ -42,7 +42,7 @@ PROTOTYPES = {
     "mi_layernorm_fwd": [p, i, p, p, p, i, p, p, i, i, f, p, p],
     "mi_layernorm_bwd": [p, i, p, i, p, p, p, p, i, i, p, p, i, i, p],
     "mi_lattice_ip": [p, p, i, p],
-    "mi_lattice_linear": [p, p, p, p, i, i, i, p],
+    "mi_lattice_linear": [p, p, p, p, i, i, i, i, ll, ll, ll, p],
     "mi_bmm3": [p, p, p, i, i, p],
     "mi_time_embed": [p, p, i, i, p, p],
     "mi_lattice_params_to_matrix": [p, p, p, i, p],

@@ -383,10 +383,15 @@ __global__ void lattice_ip_kernel(const float* __restrict__ L, float* __restrict
     ips[t] = l[3 * r] * l[3 * c] + l[3 * r + 1] * l[3 * c + 1] + l[3 * r + 2] * l[3 * c + 2];
 }
 // out[b][n] = bias[n] + sum_k vec(L_b L_b^T)[k] * W[n][k]   (the lattice part of the first edge linear, cspnet.py:67-72)
+// blockIdx.y = weight set (layer): W, bias and out advance by their strides, the lattices are shared
 __global__ void lattice_linear_kernel(const float* __restrict__ L, const float* __restrict__ W, const float* __restrict__ bias,
-                                      float* __restrict__ out, int ldo, int H) {
+                                      float* __restrict__ out, int ldo, int H, long long w_stride, long long b_stride,
+                                      long long out_stride) {
     __shared__ float ip[9];
     const int b = blockIdx.x;
+    W += blockIdx.y * w_stride;
+    if (bias) bias += blockIdx.y * b_stride;
+    out += blockIdx.y * out_stride;
     if (threadIdx.x < 9) {
         const float* l = L + 9 * b;
         int r = threadIdx.x / 3, c = threadIdx.x % 3;
@@ -834,10 +839,11 @@ extern "C" int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stre
     return MI_OK;
 }
 extern "C" int mi_lattice_linear(const float* L, const float* W, const float* bias, float* out, int ldo, int B, int H,
+                                 int n_sets, long long w_stride, long long bias_stride, long long out_stride,
                                  mi_stream_t stream) {
-    if (B <= 0) return MI_OK;
+    if (B <= 0 || n_sets <= 0) return MI_OK;
     MI_CHECK_ARG(L && W && out && H > 0 && ldo >= H, "bad arguments");
-    lattice_linear_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(L, W, bias, out, ldo, H);
+    lattice_linear_kernel<<<dim3(B, n_sets), 128, 0, (cudaStream_t)stream>>>(L, W, bias, out, ldo, H, w_stride, bias_stride, out_stride);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

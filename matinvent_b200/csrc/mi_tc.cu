@@ -31,7 +31,10 @@
 namespace {
 
 constexpr int TM = 128;                              // CTA tile rows; columns TN in {128, 64} (template)
-constexpr int TC_THREADS = 512;   // w0 TMA, w1 MMA, w2..7 operand split, w8..15 epilogue; 16 warps leave 128 registers per thread
+// Warp roles: w0 TMA, w1 MMA, then
+//   A split in the kernel : w2..7 operand split, w8..15 epilogue (16 warps: 128 registers per thread)
+//   A pre-split (PRESPLIT): w2..3 idle, w4..19 epilogue — sixteen epilogue warps, because that kernel's epilogue carries the
+//                           row gathers of the first per-edge block and is latency-bound with eight (96 registers per thread)
 constexpr int SPLIT_THREADS = 192;
 constexpr int TK = 32;                               // k-block: 32 elements = 128 B of fp32, 64 B of fp16
 // MERGED = 0: two accumulators per tile (main, 2^11-scaled correction), TN <= 128.
@@ -52,14 +55,17 @@ struct Cfg {
     static constexpr int A_H = TM * TK * 2;                       // 8 KB fp16 tile, x2 (hi, lo)
     static constexpr int W_H = TN * TK * 2;                       // fp16 weight tile, x2
     static constexpr int OPB = 2 * A_H + 2 * W_H;                 // one op-ring slot
-    static constexpr int RING_BUDGET = 192 * 1024;
+    static constexpr int EPI_WARPS = PRESPLIT ? 16 : 8;
+    static constexpr int EPI_WARP0 = PRESPLIT ? 4 : 8;            // first epilogue warp
+    static constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+    static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
+    static constexpr int EBUF_BYTES = EPI_WARPS * 32 * EPITCH * 4;   // per-warp transpose buffers of the epilogue
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int RING_BUDGET = 232448 - EBUF_BYTES - BAR_BYTES - 128;
     static constexpr int R = PRESPLIT ? 0 : (TN == 256 ? 3 : 4);
     static constexpr int S_FIT = (RING_BUDGET - R * A_RAW) / OPB;
     static constexpr int S = S_FIT > 6 ? 6 : S_FIT;
     static constexpr int RAW_BYTES = R * A_RAW, OP_BYTES = S * OPB;
-    static constexpr int EPITCH = 34;                             // floats per transpose-buffer row (float2 accesses, conflict-free)
-    static constexpr int EBUF_BYTES = 8 * 32 * EPITCH * 4;        // per-warp transpose buffers of the epilogue
-    static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = RAW_BYTES + OP_BYTES + EBUF_BYTES + BAR_BYTES + 128 /*row exponents*/;
     static constexpr uint32_t ACC_COLS = MERGED ? TN : 2 * TN;    // accumulator columns of one tile
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;           // double buffered: tile t+1 accumulates while t drains
@@ -186,7 +192,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // flight (with all four operand sets live the register allocator serialised the gathers: 15k cycles per 32x32 chunk).
 // bias / SiLU / column scales stay runtime flags.
 template <int TN, int EPI, int MERGED, int PRESPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<TN, MERGED, PRESPLIT>::THREADS), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  (n fastest, so the CTAs that share an A row
@@ -200,7 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
     uint8_t* raw_ring = smem;
     uint8_t* op_ring = smem + C::RAW_BYTES;
-    float* ebuf_all = reinterpret_cast<float*>(smem + C::RAW_BYTES + C::OP_BYTES);      // 8 warps x 32 x EPITCH floats
+    float* ebuf_all = reinterpret_cast<float*>(smem + C::RAW_BYTES + C::OP_BYTES);      // EPI_WARPS x 32 x EPITCH floats
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RAW_BYTES + C::OP_BYTES + C::EBUF_BYTES);
     uint64_t* w_full = bars;                       // [S] TMA landed in the op slot (W, and A hi/lo when PRESPLIT)
     uint64_t* a_ready = bars + S;                  // [S] split warps have written A hi/lo
@@ -215,9 +221,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (p.K + TK - 1) / TK;
     const int tiles_n = (p.N + TN - 1) / TN;
-    const int num_tiles = tiles_n * ((p.M + TM - 1) / TM);
+    const int tiles_m = (p.M + TM - 1) / TM;
+    const int num_tiles = tiles_n * tiles_m;
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)nkb;        // k-blocks this CTA goes through
+    auto tile_origin = [&](int tl, int& m0, int& n0) {
+        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+        m0 = (tile / tiles_n) * TM;
+        n0 = (tile % tiles_n) * TN;
+    };
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -232,7 +244,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 256);
+            mbar_init(&acc_empty[b], C::EPI_WARPS * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -260,8 +272,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             TRACE(0, 14);
             auto issue_raw = [&](uint32_t idx) {
                 const int tl = (int)(idx / (uint32_t)nkb), kb = (int)(idx % (uint32_t)nkb);
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int m0 = (tile / tiles_n) * TM;
+                int m0, n0;
+                tile_origin(tl, m0, n0);
                 const int r = (int)(idx % (uint32_t)RR);
                 mbar_wait(&raw_empty[r], ((idx / (uint32_t)RR) & 1) ^ 1);
                 mbar_expect_tx(&raw_full[r], A_RAW);
@@ -272,8 +284,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (; a_it + 1 < (uint32_t)R && a_it < total; ++a_it) issue_raw(a_it);
             for (uint32_t it = 0; it < total; ++it) {
                 const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
-                const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-                const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
+                int m0, n0;
+                tile_origin(tl, m0, n0);
                 const int s = (int)(it % (uint32_t)S);
                 mbar_wait(&op_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
                 if (kb == 0) TRACE(tl, 0);
@@ -321,14 +333,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 TRACE(tl, 3);
             }
         }
-    } else if (warp < 8) {
-        // ===================== operand split warps (w2..7) =====================
+    } else if (warp < C::EPI_WARP0) {
+        // ===================== operand split warps (w2..7; idle when A arrives pre-split) =====================
         const int t = threadIdx.x - 64;     // 0..191
         const mi_epilogue_t& e = p.e;
         uint32_t it = 0;
         for (int tl = 0; tl < my_tiles && !PRESPLIT; ++tl) {
-            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int m0 = (tile / tiles_n) * TM;
+            int m0, n0;
+            tile_origin(tl, m0, n0);
             // Row rescaling (fp32 dynamic range on the fp16 tensor path): when the producer of A reports the row
             // maxima, every row is multiplied by the power of two that brings its max |a| into [2^14, 2^15) before
             // the split — exact — and the result row by the inverse in the epilogue.
@@ -390,14 +402,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ===================== epilogue warps (w8..15), overlapped with the next tile's main loop =====================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int hf = (warp - 8) >> 2;              // column half handled by this warp
+        const int cg = (warp - C::EPI_WARP0) >> 2;   // column group handled by this warp
         constexpr int EP = C::EPITCH;
-        float* ebuf = ebuf_all + (warp - 8) * (32 * EP);
+        float* ebuf = ebuf_all + (warp - C::EPI_WARP0) * (32 * EP);
         const mi_epilogue_t& e = p.e;
-        constexpr int CH = TN / 64;                  // 32-column chunks per warp
+        constexpr int NCH = TN / 32, NCG = C::EPI_WARPS / 4;     // 32-column chunks of a tile, column groups of warps
+        constexpr int CH = NCH >= NCG ? NCH / NCG : 1;           // chunks per warp (narrow tiles leave column groups >= NCH idle)
         for (int tl = 0; tl < my_tiles; ++tl) {
-            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int m0 = (tile / tiles_n) * TM, n0 = (tile % tiles_n) * TN;
+            int m0, n0;
+            tile_origin(tl, m0, n0);
             const uint32_t ab = (uint32_t)tl & 1;
             const uint32_t acc = tmem_base + ab * C::ACC_COLS;
             // ---- epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global traffic
@@ -428,14 +441,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // (one accumulator, no gather operands).
             constexpr bool PREFETCH = MERGED && !(EPI & 1);
             uint32_t v[32], w[32];
-            const uint32_t tbase = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * CH * 32);
+            const uint32_t tbase = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CH * 32);
             if (PREFETCH) tmem_ld32(tbase, v);
 #pragma unroll 1
             for (int cc = 0; cc < CH; ++cc) {
-                const int nb = n0 + (hf * CH + cc) * 32;
+                const int nb = n0 + (cg * CH + cc) * 32;
                 const int col4 = (lane & 7) * 4;
                 const int n = nb + col4;
-                const bool live = nb < p.N;              // warp-uniform
+                const bool live = nb < p.N && cg * CH + cc < NCH;      // warp-uniform
                 const bool fast = live && p.c_vec && nb + 32 <= p.N;
                 // Row gathers g1 / g2 of the chunk: 2 x 4 x 16-byte loads per lane and half chunk, issued so that their
                 // L2 round trips hide behind the TMEM read + transpose (first half) and behind the first half's
@@ -451,7 +464,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (e.g2) gb[u] = ldg_stream4(e.g2 + (long long)r2 * e.g2_ld + n);
                     }
                 };
-                if (!PREFETCH) {
+                if (!PREFETCH && cg * CH + cc < NCH) {
                     tmem_ld32(tbase + (uint32_t)(cc * 32), v);
                     if (!MERGED) tmem_ld32(tbase + (uint32_t)(cc * 32) + CORR, w);
                 }
@@ -681,7 +694,7 @@ int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, con
     }
     const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM);
     const int grid = (int)(tiles < sms ? tiles : sms);        // persistent: one CTA per SM
-    tc_gemm_kernel<TN, EPI, MERGED, PRESPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
+    tc_gemm_kernel<TN, EPI, MERGED, PRESPLIT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

@@ -48,8 +48,9 @@ class _Workspace:
         self.phi_lo = torch.empty(E, F6, device=dev, dtype=torch.float16)
         self.ips = buf(B, 9)
         self.tb = buf(B, H)
-        self.cb2 = torch.zeros(B, 2 * H, device=dev, dtype=f32)   # [C_b | 0]: folded into P by the P|Q GEMM's epilogue
-        self.cb = self.cb2[:, :H]
+        # [C_b | 0] of every layer: folded into P by the P|Q GEMM's epilogue (one launch fills all layers: the lattices
+        # do not change inside a forward)
+        self.cb2 = torch.zeros(net.num_layers, B, 2 * H, device=dev, dtype=f32)
         self.h0 = buf(N, H)
         self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] * (L + 1)
         self.cat = [buf(N, 2 * H) for _ in range(nl)]
@@ -408,6 +409,11 @@ class CSPNet(nn.Module):
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
                          ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
                          op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
+        # per-crystal term C_b of the first edge linear, all layers in one launch (the layer blocks of the flat weight
+        # buffer are equally spaced)
+        lstride = (self._slices["l1.w_l"][0] - self._slices["l0.w_l"][0]) if L > 1 else 0
+        ops.lattice_linear(l, W["l0.w_l"], W["l0.b1"], ws.cb2[0, :, :H], B, H, n_sets=L, w_stride=lstride,
+                           bias_stride=lstride, out_stride=ws.cb2.stride(0))
         for i in range(L):
             q = "l%d." % i
             k = i if train else 0
@@ -425,8 +431,7 @@ class CSPNet(nn.Module):
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
             # per-crystal term C_b first, folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the
             # per-edge GEMM then adds two gathered rows instead of three
-            ops.lattice_linear(l, W[q + "w_l"], W[q + "b1"], ws.cb, B, H)
-            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2, g.node_graph)])
+            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2[i], g.node_graph)])
             self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
             self.edge_gemm2(i, ws, E, a1, train, merged)
             # scatter-mean over the source node (cspnet.py:79)

@@ -219,10 +219,13 @@ def lattice_ip(L, ips, B):
     return ips
 
 
-def lattice_linear(L, W, bias, out, B, H):
+def lattice_linear(L, W, bias, out, B, H, n_sets=1, w_stride=0, bias_stride=0, out_stride=0):
+    """out[s][b] = bias_s + vec(L_b L_b^T) W_s^T for n_sets weight sets spaced by the given element strides
+    (W, bias: views of set 0; out: view of set 0 with row stride _ld(out)).  See mi_lattice_linear."""
     for t in (L, W, bias, out):
         _f32(t)
-    check(lib().mi_lattice_linear(_p(L), _p(W), _p(bias), _p(out), _ld(out), B, H, _stream()), "mi_lattice_linear")
+    check(lib().mi_lattice_linear(_p(L), _p(W), _p(bias), _p(out), _ld(out), B, H, n_sets, w_stride, bias_stride,
+                                  out_stride, _stream()), "mi_lattice_linear")
     return out
 
 

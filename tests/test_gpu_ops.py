@@ -187,6 +187,15 @@ def test_small_per_crystal_ops(ops):
     cb = torch.empty(B, 512, device="cuda")
     ops.lattice_linear(L, Wl, bl, cb, B, 512)
     assert rel_err(cb, (L.double() @ L.double().transpose(1, 2)).view(B, 9) @ Wl.double().t() + bl.double()) < 1e-6
+    # three equally spaced weight sets (the layers of the flat weight buffer) in one launch, strided output
+    flat = _rand(3, 6000, seed=35)
+    Ws, bs = flat[0, :4608].view(512, 9), flat[0, 4608:5120]
+    cbs = torch.zeros(3, B, 1024, device="cuda")
+    ops.lattice_linear(L, Ws, bs, cbs[0, :, :512], B, 512, n_sets=3, w_stride=6000, bias_stride=6000, out_stride=cbs.stride(0))
+    for k in range(3):
+        ref = (L.double() @ L.double().transpose(1, 2)).view(B, 9) @ flat[k, :4608].view(512, 9).double().t() + flat[k, 4608:5120].double()
+        assert rel_err(cbs[k, :, :512], ref) < 1e-6
+    assert float(cbs[:, :, 512:].abs().max()) == 0.0
     A = _rand(B, 3, 3, seed=30)
     out = torch.empty(B, 3, 3, device="cuda")
     ops.bmm3(A, L, out, B)
