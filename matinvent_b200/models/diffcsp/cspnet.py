@@ -431,7 +431,9 @@ class CSPNet(nn.Module):
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
             # per-crystal term C_b first, folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the
             # per-edge GEMM then adds two gathered rows instead of three
-            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2[i], g.node_graph)])
+            # (amax_agg[i] holds the row maxima of LN(h) only at this point: the scatter adds its own further down)
+            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2[i], g.node_graph)],
+                         a_amax=ws.amax_agg[i])
             self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
             self.edge_gemm2(i, ws, E, a1, train, merged)
             # scatter-mean over the source node (cspnet.py:79)

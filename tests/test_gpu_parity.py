@@ -290,3 +290,75 @@ def test_knn_gradients_vs_oracle_autograd(gold_small):
     grads = m.decoder.reference_named_grads()
     worst = max((rel_err(grads[k], v.grad), k) for k, v in sd.items())
     assert worst[0] < 1e-4, worst
+
+
+# ---------------------------------------------------------------- BASELINE batch (256 mp_20 crystals, ~34k edges)
+# The golden cases above hold 4 crystals (601 edges): the per-edge GEMMs take the two-accumulator 128x128 tiles there.
+# At the benchmark's batch they switch to the single-accumulator 128x256 tiles (CSPNet.edge_mode), so that path is
+# pinned here: one forward against the oracle on the same inputs, gradients and a reverse trajectory against the
+# FP32 CUDA-core path, which the golden cases above pin to the unmodified reference.
+def _baseline_batch(seed=0):
+    import numpy as np
+    from matinvent_b200.models.diffcsp.sample import ATOM_DIST
+    na = torch.tensor(np.random.RandomState(0).choice(21, 256, p=ATOM_DIST["mp_20"]).tolist())
+    g = torch.Generator().manual_seed(seed)
+    N, B = int(na.sum()), len(na)
+    t = torch.randn(B, 256, generator=g)
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g) + 4.0 * torch.eye(3)
+    return na, t, a, x, l
+
+
+def test_forward_baseline_batch_vs_oracle(gold_full):
+    from oracle import diffcsp_oracle as O
+    m = _full_module(gold_full)
+    na, t, a, x, l = _baseline_batch()
+    n2g = torch.repeat_interleave(torch.arange(len(na)), na)
+    dec = m.decoder
+    assert dec.edge_mode(int((na * na).sum())) == (True, True)          # merged tiles are what runs here
+    with torch.no_grad():
+        pl, px, pt = dec(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+    sd = O.init_params(gold_full["hp"], gold_full["seeds"][0])
+    with torch.no_grad():
+        rl, rx, rt = O.cspnet_forward(sd, gold_full["hp"], t, a, x, l, na, n2g)
+    errs = (rel_err(pl, rl), rel_err(px, rx), rel_err(pt, rt))
+    print("baseline-batch forward vs oracle: lattice %.2e coord %.2e type %.2e" % errs)
+    assert max(errs) < 2e-5, errs
+
+
+def test_gradients_baseline_batch_merged_vs_ffma(gold_full):
+    """training forward (pre-activation stores) + hand-written backward at the benchmark's batch: tensor-core
+    (merged tiles) against the FP32 CUDA-core path"""
+    na, t, a, x, l = _baseline_batch(1)
+    n2g = torch.repeat_interleave(torch.arange(len(na)), na)
+    grads = []
+    for use_tc in (True, False):
+        m = _full_module(gold_full)
+        m.decoder.use_tc = use_tc
+        pl, px, pt = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+        g = torch.Generator().manual_seed(5)
+        wl, wx, wt = (torch.randn(p.shape, generator=g).cuda() for p in (pl, px, pt))
+        ((pl * wl).sum() + (px * wx).sum() + (pt * wt).sum()).backward()
+        grads.append({k: v.clone() for k, v in m.decoder.reference_named_grads().items()})
+    worst = max((rel_err(grads[0][k], grads[1][k]), k) for k in grads[0])
+    print("baseline-batch gradients, merged tensor-core vs FFMA: worst %.2e (%s)" % worst)
+    assert worst[0] < 1e-4, worst
+
+
+def test_sample_baseline_batch_merged_vs_ffma(gold_full):
+    """60 reverse steps (end of the schedule, where the score network matters most) of the 256-crystal batch on a
+    shared noise tape: tensor-core (merged tiles) against the FP32 CUDA-core path, same 1e-4 bar as the golden case"""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    na = _baseline_batch()[0]
+    outs = []
+    for use_tc in (True, False):
+        m = _full_module(gold_full)
+        m.decoder.use_tc = use_tc
+        out, _ = m.sample(make_batch(na.tolist()), step_lr=1e-5, noise=TapeNoise("cuda", seed=11), timesteps=60)
+        outs.append(out)
+    ef, el = wrapped_err(outs[0]["frac_coords"], outs[1]["frac_coords"]), rel_err(outs[0]["lattices"], outs[1]["lattices"])
+    print("baseline-batch 60-step sample, merged tensor-core vs FFMA: frac %.2e lattice %.2e" % (ef, el))
+    assert ef < 1e-4 and el < 1e-4
+    assert torch.equal(_types(outs[0]["atom_types"]), _types(outs[1]["atom_types"]))
