@@ -279,17 +279,19 @@ def main():
     ach_pair = fl_pair / t_pair / 1e12
     kname = "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)"
     # DRAM traffic of this launch from the committed ncu --set full capture of the default workload
-    # (profiles/r1_final_tc_gemm_ncu_raw.csv: dram__bytes_read.sum 118.8 MB + dram__bytes_write.sum 36.0 MB)
-    traffic = 154.8e6 if (dec.use_tc and g.E == 34445) else None
+    # (profiles/r1b_tc_gemm_ncu_raw.csv, tc_gemm_kernel<256,1,1,1>: dram__bytes_read.sum 123.3 MB + dram__bytes_write.sum 35.6 MB)
+    traffic = 158.9e6 if (dec.use_tc and merged and g.E == 34445) else None
     roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM 1 (Phi.W_F^T + 2 gathered rows + SiLU), the largest launch",
                     achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
                     flop_per_launch=fl_g1, us_per_launch=t_g1,
                     algorithmic_bytes_per_launch=2 * 2 * g.E * F6 + 4 * g.E * H + 2 * 2 * H * F6 + 2 * 4 * g.N * 2 * H,
                     peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                     note="achieved = algorithmic FP32 FLOPs / CUDA-event time of the launch; FP32-grade accuracy costs 3 fp16 MMAs per "
-                         "product (x = hi + 2^-11 lo), so the ceiling of frac is 1/3 (1e-4 parity over 2000 chained forwards rules out "
-                         "plain TF32/BF16/FP16 inputs); edge GEMM pair (this launch + the K=512 one): %.1f TFLOP/s, share of step = %.2f"
-                         % (ach_pair, 2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
+                         "product (x = hi + lo), so the ceiling of frac is 1/3 (1e-4 parity over 2000 chained forwards rules out "
+                         "plain TF32/BF16/FP16 inputs); tiles: %s; edge GEMM pair (this launch + the K=512 one): %.1f TFLOP/s, "
+                         "share of step = %.2f"
+                         % ("128x256, one accumulator" if merged else "128x128, main + correction accumulators", ach_pair,
+                            2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
                     mma_tflops=3 * ach, frac_mma_of_peak=3 * ach / peak_tf, us_gemm1=t_g1, us_gemm2=t_g2)
     # the edge-scatter (segment-mean) kernel against the HBM roofline, in isolation, L2 flushed between launches
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
