@@ -235,16 +235,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (smem_u32(smem) & 1023u) __trap();
         for (int s = 0; s < S; ++s) {
             mbar_init(&w_full[s], 1);
-            mbar_init(&a_ready[s], SPLIT_THREADS);
+            mbar_init(&a_ready[s], SPLIT_THREADS / 32);     // one arrive per split warp
             mbar_init(&op_empty[s], 1);
         }
         for (int r = 0; r < R; ++r) {
             mbar_init(&raw_full[r], 1);
-            mbar_init(&raw_empty[r], SPLIT_THREADS);
+            mbar_init(&raw_empty[r], SPLIT_THREADS / 32);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], C::EPI_WARPS * 32);
+            mbar_init(&acc_empty[b], C::EPI_WARPS);         // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -391,9 +391,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 // Release the raw slot only now: the stores above consumed every loaded register, so the LDS results
                 // have landed.  (An arrive issued right behind the LDS instructions overtook them, and TMA refilled
                 // the slot under the loads now and then.)
-                mbar_arrive(&raw_empty[r]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-                mbar_arrive(&a_ready[s]);
+                __syncwarp();                                                   // every lane's stores and fence are done
+                if (lane == 0) {
+                    mbar_arrive(&raw_empty[r]);
+                    mbar_arrive(&a_ready[s]);
+                }
 #ifdef MI_TC_TRACE
                 if (t == 0 && kb == 0) TRACE(tl, 13);
 #endif
@@ -473,7 +476,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (threadIdx.x == 320 && cc < 4) TRACE(tl, 5 + cc);
                 if (cc == CH - 1) {                      // all of this warp's TMEM reads are done: release the accumulators
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[ab]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[ab]);
                 }
                 if (live) {
 #pragma unroll
