@@ -187,8 +187,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the ONE JSON line and nothing else: NCCL writes its version banner to file descriptor 1 when the
+    # communicator comes up (NCCL_DEBUG_FILE does not catch it on every box), so fd 1 points at stderr for the whole
+    # run and the result goes out through the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the ONE JSON line (NCCL prints its version there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from matinvent_b200 import _lib
@@ -345,7 +351,7 @@ def main():
         cb, _ = cpu_reference_leg(na_all, m.decoder.state_dict())
 
     if rank == 0:
-        print(json.dumps(dict(
+        line = (json.dumps(dict(
             metric="crystals/sec sampled (1000-step reverse)", value=value, unit="crystals/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -358,6 +364,8 @@ def main():
                         parallelism="dp%d (crystals sharded, no collective while sampling)" % world),
             clocks=clk, gpu_launches=gpu_launches, launches_per_reverse_step=per_step_launches,
             e2e=e2e, roofline=roofline, roofline_edge_scatter=roofline_scatter, cpu_baseline=cb)))
+        sys.stdout.flush()
+        os.write(json_fd, (line + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

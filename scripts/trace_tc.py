@@ -13,7 +13,7 @@ if sys.argv[1] == "build":
 os.environ["MATINVENT_B200_LIB"] = TRACE_LIB
 import torch
 from matinvent_b200 import ops, _lib
-M, N, K = 34445, 512, int(os.environ.get("K", "512"))
+M, N, K = int(os.environ.get("M", "34445")), int(os.environ.get("N", "512")), int(os.environ.get("K", "512"))
 merged = int(os.environ.get("MERGED", "1"))
 act = int(os.environ.get("ACT", "1"))
 A, W = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") / K ** 0.5
@@ -22,7 +22,7 @@ hi, lo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=tor
 s = ops.merged_scale(W) if merged else 1.0
 ops.f16_split(W, hi, lo, s, 1.0 if merged else 2048.0)
 C = torch.empty(M, N, device="cuda")
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush = torch.empty((256 << 20) if int(os.environ.get("FLUSH", "1")) else 16, dtype=torch.uint8, device="cuda")
 gemm1 = int(os.environ.get("GEMM1", "0"))      # the first per-edge block: pre-split A, two gathers, row maxima
 if gemm1:
     Ahi = torch.empty(M, K, device="cuda", dtype=torch.float16)
