@@ -362,3 +362,44 @@ def test_sample_baseline_batch_merged_vs_ffma(gold_full):
     print("baseline-batch 60-step sample, merged tensor-core vs FFMA: frac %.2e lattice %.2e" % (ef, el))
     assert ef < 1e-4 and el < 1e-4
     assert torch.equal(_types(outs[0]["atom_types"]), _types(outs[1]["atom_types"]))
+
+
+# ---------------------------------------------------------------- ragged / degenerate batches against the oracle
+@pytest.mark.parametrize("num_atoms", [[1], [1, 1, 1], [20, 20, 20], [1, 20, 1, 7], [2] * 65, [20] * 33])
+def test_forward_ragged_batches_vs_oracle(gold_small, num_atoms):
+    """single-atom crystals (one self edge each), the maximum of the mp_20 prior (20 atoms), a one-crystal batch and
+    batches whose node / edge counts straddle the 128-row tiles: forward against the oracle on the same inputs"""
+    from oracle import diffcsp_oracle as O
+    gs = gold_small
+    hp, sd = gs["hp"], gs["sd"]
+    m = build_module(hp, sd, gs["sigmas_norm"])
+    na = torch.tensor(num_atoms)
+    g = torch.Generator().manual_seed(17 + len(num_atoms))
+    N, B = int(na.sum()), len(na)
+    t = torch.randn(B, hp["time_dim"], generator=g)
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g) + 4.0 * torch.eye(3)
+    n2g = torch.repeat_interleave(torch.arange(B), na)
+    with torch.no_grad():
+        pl, px, pt = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+        rl, rx, rt = O.cspnet_forward(sd, hp, t, a, x, l, na, n2g)
+    assert pl.shape == rl.shape and px.shape == rx.shape and pt.shape == rt.shape
+    assert max(rel_err(pl, rl), rel_err(px, rx), rel_err(pt, rt)) < 2e-5
+
+
+@pytest.mark.parametrize("num_atoms", [[1], [1, 20, 1]])
+def test_sample_degenerate_batches_vs_oracle(gold_small, num_atoms):
+    """a 12-step reverse trajectory of degenerate batches on a shared noise tape, CUDA-graph path, against the oracle"""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle import diffcsp_oracle as O
+    from oracle.ref_import import make_batch
+    gs = gold_small
+    hp, sd = gs["hp"], gs["sd"]
+    m = build_module(hp, sd, gs["sigmas_norm"])
+    out, _ = m.sample(make_batch(num_atoms), step_lr=1e-5, noise=TapeNoise("cuda", seed=3), timesteps=12)
+    ref = O.sample(sd, hp, O.Schedules(hp, gs["sigmas_norm"]), num_atoms, O.Noise(torch.Generator().manual_seed(3)),
+                   step_lr=1e-5, timesteps=12)
+    assert wrapped_err(out["frac_coords"], ref["frac_coords"]) < 1e-4
+    assert rel_err(out["lattices"], ref["lattices"]) < 1e-4
+    assert torch.equal(_types(out["atom_types"]), _types(ref["atom_types"]))
