@@ -75,7 +75,7 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
 /* Tensor-core variant for the forward dense blocks (A [M,K] and W [N,K] both K-contiguous, i.e.
  * transA = 0, transB = 1): FP32-grade product by split-precision FP16 on tcgen05 (x = x_hi + x_lo, three
  * MMAs per k-slice, TMA-staged swizzled operand tiles, TMEM accumulators), same epilogue contract as
- * mi_sgemm (no split-K).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
+ * mi_sgemm (no split-K, no beta; MI_ACT_DSILU only without gathers / z_out / g3 / resid).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
  * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo.
  *
  * Two operand formats (flags):
@@ -138,9 +138,10 @@ int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, 
 
 /* dX[e][:] = dOut[idx[e]][:] * (inv_count ? 1/max(cnt(idx[e]),1) : 1) * (z ? silu'(z[e][:]) : 1)
  * (backward of segment mean + SiLU).  idx nullable -> identity; ptr = CSR used for counts (nullable ->
- * no scaling). */
+ * no scaling).  amax_out (nullable, [E], caller zeroes it) receives max |dX[e][:]| for the row rescaling of the
+ * tensor-core GEMM that consumes dX. */
 int mi_gather_rows_dsilu(const float* dOut, int ldd, const int* idx, const int* ptr, const float* z,
-                         int ldz, float* dX, int ldx, int E, int H, mi_stream_t stream);
+                         int ldz, float* dX, int ldx, int E, int H, float* amax_out, mi_stream_t stream);
 
 /* out[n] (+)= sum_m X[m][n]  (bias gradients) */
 int mi_colsum(const float* X, int ldx, int M, int N, float* out, int accumulate, mi_stream_t stream);

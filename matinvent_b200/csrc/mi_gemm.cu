@@ -165,9 +165,17 @@ __global__ void __launch_bounds__(NT, 2) sgemm_kernel(const GemmParams p) {
             float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
             float* crow = p.C + (long long)m * p.ldc + n;
             if (atomic) {
+                if (p.c_vec && n + 3 < p.N) {
+                    // one 16-byte reduction instead of four scalar atomics: the weight-gradient GEMMs of the fine-tune
+                    // step (K split 11 ways at the reference's batch) were bound by L2 atomic throughput
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow), "f"(e.alpha * v[0]), "f"(e.alpha * v[1]),
+                                 "f"(e.alpha * v[2]), "f"(e.alpha * v[3])
+                                 : "memory");
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n + j < p.N) atomicAdd(crow + j, e.alpha * v[j]);
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < p.N) atomicAdd(crow + j, e.alpha * v[j]);
+                }
                 continue;
             }
             if (p.c_vec && n + 3 < p.N) {

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __rest
 
 __global__ void gather_rows_dsilu_kernel(const float* __restrict__ dOut, int ldd, const int* __restrict__ idx,
                                          const int* __restrict__ ptr, const float* __restrict__ z, int ldz,
-                                         float* __restrict__ dX, int ldx, int E, int H4) {
+                                         float* __restrict__ dX, int ldx, int E, int H4, float* __restrict__ amax_out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)E * H4) return;
     int e = (int)(t / H4), c = (int)(t - (long long)e * H4);
@@ -260,6 +260,16 @@ __global__ void gather_rows_dsilu_kernel(const float* __restrict__ dOut, int ldd
         g.x *= mi_dsilu(zz.x); g.y *= mi_dsilu(zz.y); g.z *= mi_dsilu(zz.z); g.w *= mi_dsilu(zz.w);
     }
     *(reinterpret_cast<float4*>(dX + (long long)e * ldx) + c) = g;
+    if (amax_out) {          // row maxima for the tensor-core GEMM that consumes dX (gradients span many binades)
+        float m = fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w)));
+        if ((H4 & 31) == 0) {                     // a warp stays inside one row
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(amax_out + e), __float_as_uint(m));
+        } else {
+            atomicMax(reinterpret_cast<unsigned*>(amax_out + e), __float_as_uint(m));
+        }
+    }
 }
 
 // out[n] += sum over a slab of rows; block (32, 8), grid (ceil(N/32), slabs)
@@ -778,12 +788,12 @@ extern "C" int mi_segment_reduce(const float* X, int ldx, const int* ptr, const 
 }
 
 extern "C" int mi_gather_rows_dsilu(const float* dOut, int ldd, const int* idx, const int* ptr, const float* z,
-                                    int ldz, float* dX, int ldx, int E, int H, mi_stream_t stream) {
+                                    int ldz, float* dX, int ldx, int E, int H, float* amax_out, mi_stream_t stream) {
     MI_CHECK_ARG(E >= 0 && H > 0 && H % 4 == 0 && ldd % 4 == 0 && ldx % 4 == 0 && (!z || ldz % 4 == 0), "sizes must be multiples of 4");
     if (E == 0) return MI_OK;
     MI_CHECK_ARG(dOut && dX, "null pointer");
     long long n = (long long)E * (H / 4);
-    gather_rows_dsilu_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(dOut, ldd, idx, ptr, z, ldz, dX, ldx, E, H / 4);
+    gather_rows_dsilu_kernel<<<mi_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(dOut, ldd, idx, ptr, z, ldz, dX, ldx, E, H / 4, amax_out);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

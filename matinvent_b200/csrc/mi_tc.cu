@@ -141,6 +141,11 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     return v;
 }
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// d/dx [x sigmoid(x)] = s (1 + x (1 - s)), same approximations
+__device__ __forceinline__ float dsilu_fast(float x) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+    return s * fmaf(x, 1.0f - s, 1.0f);
+}
 // x -> (fp16(x), fp16((x - fp16(x)) * 2^11)) packed for two consecutive elements
 template <int MERGED>
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -188,7 +193,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // EPI bit 0: row gathers g1 / g2 present, bit 1: pre-activation store (training), bit 2: third gather g3 and / or
-// residual present.  Compile-time so that the epilogue of the hot instantiations keeps every load of a batch in
+// residual present; EPI = 8: SiLU' epilogue of the backward (v * silu'(z_in)), nothing else.  Compile-time so that the epilogue of the hot instantiations keeps every load of a batch in
 // flight (with all four operand sets live the register allocator serialised the gathers: 15k cycles per 32x32 chunk).
 // bias / SiLU / column scales stay runtime flags.
 template <int TN, int EPI, int MERGED, int PRESPLIT>
@@ -501,7 +506,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (e.col_scale) cs4 = __ldg(reinterpret_cast<const float4*>(e.col_scale + n));
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        float4 gc[4], gr[4];
+                        float4 gc[4], gr[4], gz[4];
                         float2 xa[4], xb[4];
                         int mm[4];
 #pragma unroll
@@ -510,7 +515,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const int m = m0 + q * 32 + rr;
                             mm[u] = m;
                             const bool ok = m < p.M;
-                            gc[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            gc[u] = gr[u] = gz[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((EPI & 8) && ok) gz[u] = ldg_stream4(e.z_in + (long long)m * e.zin_ld + n);
                             if (EPI & 4) {
                                 const int r3 = __shfl_sync(0xffffffffu, i3, rr);
                                 if (ok && e.g3) gc[u] = ldg_stream4(e.g3 + (long long)r3 * e.g3_ld + n);
@@ -532,7 +538,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             if (EPI & 4) { x[0] += gc[u].x; x[1] += gc[u].y; x[2] += gc[u].z; x[3] += gc[u].w; }
                             if (EPI & 2) *reinterpret_cast<float4*>(e.z_out + (long long)m * e.z_ld + n) = make_float4(x[0], x[1], x[2], x[3]);
-                            if (e.act == MI_ACT_SILU) {
+                            if (EPI & 8) {                 // backward of SiLU: v * silu'(z_in)
+                                x[0] *= dsilu_fast(gz[u].x); x[1] *= dsilu_fast(gz[u].y);
+                                x[2] *= dsilu_fast(gz[u].z); x[3] *= dsilu_fast(gz[u].w);
+                            } else if (e.act == MI_ACT_SILU) {
 #pragma unroll
                                 for (int v4 = 0; v4 < 4; ++v4) x[v4] = silu_fast(x[v4]);
                             }
@@ -572,7 +581,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 }
                                 if ((EPI & 4) && e.g3) y += __ldg(e.g3 + (long long)r3 * e.g3_ld + n + u);
                                 if (EPI & 2) e.z_out[(long long)m * e.z_ld + n + u] = y;
-                                if (e.act == MI_ACT_SILU) y = silu_fast(y);
+                                if (EPI & 8) y *= dsilu_fast(__ldg(e.z_in + (long long)m * e.zin_ld + n + u));
+                                else if (e.act == MI_ACT_SILU) y = silu_fast(y);
                                 if ((EPI & 4) && e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
                                 crow[u] = y;
                                 rmax = fmaxf(rmax, fabsf(y));
@@ -718,8 +728,9 @@ int dispatch_tc(int epi_mode, bool presplit, int M, int N, int K, const void* A,
         MI_TC_CASE(4)
         MI_TC_CASE(5)
         MI_TC_CASE(6)
-        default:
         MI_TC_CASE(7)
+        default:
+        MI_TC_CASE(8)
     }
 #undef MI_TC_CASE
 }
@@ -771,7 +782,10 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
         p.e = z;
     }
     MI_CHECK_ARG(p.e.splitk <= 1, "split-K is not available on the tensor-core path");
-    MI_CHECK_ARG(p.e.act != MI_ACT_DSILU && p.e.beta == 0.f, "the tensor-core path has no DSILU / accumulate epilogue (use mi_sgemm)");
+    MI_CHECK_ARG(p.e.beta == 0.f, "the tensor-core path has no accumulate epilogue (pass C as resid, or use mi_sgemm)");
+    if (p.e.act == MI_ACT_DSILU)
+        MI_CHECK_ARG(p.e.z_in && !p.e.g1 && !p.e.g2 && !p.e.g3 && !p.e.z_out && !p.e.resid,
+                     "MI_ACT_DSILU on the tensor-core path needs z_in and a plain epilogue otherwise");
     bool cv = (ldc % 4 == 0) && mi_host_aligned16(C);
     const mi_epilogue_t& e = p.e;
     if (e.bias) cv = cv && mi_host_aligned16(e.bias);
@@ -792,7 +806,7 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     const char* force = getenv("MI_TC_TN");
     if (force) tn = atoi(force) <= 64 ? 64 : 128;
     cudaStream_t s = (cudaStream_t)stream;
-    const int epi_mode = ((p.e.g1 || p.e.g2) ? 1 : 0) | (p.e.z_out ? 2 : 0) | ((p.e.g3 || p.e.resid) ? 4 : 0);
+    const int epi_mode = p.e.act == MI_ACT_DSILU ? 8 : (((p.e.g1 || p.e.g2) ? 1 : 0) | (p.e.z_out ? 2 : 0) | ((p.e.g3 || p.e.resid) ? 4 : 0));
     if (merged) return dispatch_tc<256, 1>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
     if (tn == 128) return dispatch_tc<128, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
     return dispatch_tc<64, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);

@@ -95,6 +95,16 @@ class _Workspace:
             self.dgn = buf(N, H)
             self.dlat9 = buf(B, 9)
             self.dtb = buf(B, H)
+            # row maxima of the gradient operands of the tensor-core input-gradient GEMMs, per layer (gradients span
+            # many binades: the fp16 split needs the power-of-two row rescaling); zeroed at the start of a backward
+            self.gamax = torch.zeros(L * (3 * N + E), device=dev, dtype=f32)
+            self.amax_dzn, self.amax_dzn1, self.amax_dz2, self.amax_dpq = [], [], [], []
+            o = 0
+            for _ in range(L):
+                self.amax_dzn.append(self.gamax[o:o + N]); o += N
+                self.amax_dzn1.append(self.gamax[o:o + N]); o += N
+                self.amax_dpq.append(self.gamax[o:o + N]); o += N
+                self.amax_dz2.append(self.gamax[o:o + E]); o += E
 
 
 class CSPNet(nn.Module):
@@ -142,6 +152,10 @@ class CSPNet(nn.Module):
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
         self._mhi, self._mlo, self._minv = {}, {}, {}
+        # transposed copies W^T (fp16 head / tail) of the weights whose input gradients run on the tensor cores
+        # (dX = dY W is the forward kernel with W^T as its weight); built once a backward has asked for them
+        self._hiT, self._loT, self._wT = {}, {}, {}
+        self._need_T = False
         self._tc_version = None
         self.reset_parameters()
 
@@ -161,6 +175,7 @@ class CSPNet(nn.Module):
         self._ws, self._graphs = {}, {}
         self._flat_hi = self._flat_lo = None
         self._mhi, self._mlo, self._minv = {}, {}, {}
+        self._hiT, self._loT, self._wT = {}, {}, {}
         self._tc_version = None
         return r
 
@@ -190,6 +205,16 @@ class CSPNet(nn.Module):
                         self._mlo[k] = torch.empty_like(w, dtype=torch.float16)
                         self._minv[k] = torch.empty(w.shape[0], device=w.device, dtype=torch.float32)
                     ops.f16_split_rows(w, self._mhi[k], self._mlo[k], self._minv[k])
+        if self._need_T:
+            for i in range(self.num_layers):
+                for k in ("l%d.wn2" % i, "l%d.wn1" % i, "l%d.w2" % i, "l%d.w_pq" % i):
+                    w = self._views[k]
+                    if k not in self._hiT:
+                        self._wT[k] = torch.empty(w.shape[1], w.shape[0], device=w.device, dtype=torch.float32)
+                        self._hiT[k] = torch.empty_like(self._wT[k], dtype=torch.float16)
+                        self._loT[k] = torch.empty_like(self._wT[k], dtype=torch.float16)
+                    self._wT[k].copy_(w.t())
+                    ops.f16_split(self._wT[k], self._hiT[k], self._loT[k])
         self._tc_version = ver
 
     def _linear(self, A, wname, C, M, **epi):
@@ -198,6 +223,17 @@ class CSPNet(nn.Module):
         if self.use_tc and ops.tc_ok(A, self._hi[wname]):
             return ops.tc_gemm(A, self._hi[wname], self._lo[wname], C, M=M, **epi)
         return ops.sgemm(A, W, C, M=M, **epi)
+
+    def _dgrad(self, dY, wname, C, M, a_amax, act=ACT_NONE, z_in=None, amax_out=None, accumulate=False):
+        """C = dY @ W (* silu'(z_in)) (+ C): input gradient of y = x W^T.  Tensor cores (the forward kernel with W^T as
+        its weight operand, rows of dY rescaled from their maxima) or the FP32 CUDA-core NN GEMM."""
+        W = self._views[wname]
+        N_out, K_in = W.shape
+        if self.use_tc and wname in self._hiT and ops.tc_ok(dY, self._hiT[wname]) and C.stride(0) % 4 == 0:
+            return ops.tc_gemm(dY, self._hiT[wname], self._loT[wname], C, M=M, act=act, z_in=z_in, a_amax=a_amax,
+                               amax_out=amax_out, resid=C if accumulate else None)
+        return ops.sgemm(dY, W, C, transB=False, M=M, N=K_in, K=N_out, act=act, z_in=z_in, beta=1.0 if accumulate else 0.0,
+                         amax_out=amax_out)
 
     @property
     def device(self):
@@ -485,6 +521,11 @@ class CSPNet(nn.Module):
         F6, T = 6 * self.num_freqs, self.latent_dim
         ws = ws or self.workspace(g, True)
         hf = ws.hf if self.ln else ws.h[L]
+        if self.use_tc and not self._need_T:
+            self._need_T = True
+            self._tc_version = None
+            self._refresh_tc()
+        ws.gamax.zero_()
         # ---- heads (cspnet.py:276-294)
         if self.ip:
             ops.bmm3(d_l, l, ws.dlat9, B, transL=True)
@@ -511,28 +552,30 @@ class CSPNet(nn.Module):
             q = "l%d." % i
             cat, a1, an1 = ws.cat[i], ws.a1[i], ws.an1[i]
             # h_out = h_in + silu(zn2);  zn2 = an1 wn2^T + bn2;  an1 = silu(zn1);  zn1 = cat wn1^T + bn1
-            ops.gather_rows_dsilu(dh, None, None, ws.zn2[i], ws.dzn, N, H)
+            ops.gather_rows_dsilu(dh, None, None, ws.zn2[i], ws.dzn, N, H, amax_out=ws.amax_dzn[i])
             self._wgrad(ws.dzn, an1, q + "wn2", H, H, N)
             ops.colsum(ws.dzn, N, H, G[q + "bn2"])
-            ops.sgemm(ws.dzn, W[q + "wn2"], ws.dzn1, transB=False, M=N, N=H, K=H, act=ACT_DSILU, z_in=ws.zn1[i])
+            self._dgrad(ws.dzn, q + "wn2", ws.dzn1, N, ws.amax_dzn[i], act=ACT_DSILU, z_in=ws.zn1[i],
+                        amax_out=ws.amax_dzn1[i])
             self._wgrad(ws.dzn1, cat, q + "wn1", H, 2 * H, N)
             ops.colsum(ws.dzn1, N, H, G[q + "bn1"])
-            ops.sgemm(ws.dzn1, W[q + "wn1"], ws.dcat, transB=False, M=N, N=2 * H, K=H)
+            self._dgrad(ws.dzn1, q + "wn1", ws.dcat, N, ws.amax_dzn1[i])
             # agg = mean_j a2 ; a2 = silu(z2) ; z2 = a1 w2^T + b2
-            ops.gather_rows_dsilu(ws.dcat[:, H:], g.edge_src, g.seg_ptr, ws.z2[i], ws.dz2, E, H)
+            ops.gather_rows_dsilu(ws.dcat[:, H:], g.edge_src, g.seg_ptr, ws.z2[i], ws.dz2, E, H, amax_out=ws.amax_dz2[i])
             self._wgrad(ws.dz2, a1, q + "w2", H, H, E)
             ops.colsum(ws.dz2, E, H, G[q + "b2"])
             # a1 = silu(z1) ; z1 = Phi w_f^T + P[src] + Q[dst] + C[graph]
-            ops.sgemm(ws.dz2, W[q + "w2"], ws.dz1, transB=False, M=E, N=H, K=H, act=ACT_DSILU, z_in=ws.z1[i])
+            self._dgrad(ws.dz2, q + "w2", ws.dz1, E, ws.amax_dz2[i], act=ACT_DSILU, z_in=ws.z1[i])
             self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E)
-            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False)
-            ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False)
+            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i])
+            ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False,
+                               amax_out=ws.amax_dpq[i])
             ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False)
             ops.colsum(ws.dcb, B, H, G[q + "b1"])
             self._wgrad(ws.dcb, ws.ips, q + "w_l", H, 9, B)
             self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N)
             # d hn = dcat[:, :H] + dpq @ w_pq   (written over dcat[:, :H])
-            ops.sgemm(ws.dpq, W[q + "w_pq"], ws.dcat[:, :H], transB=False, M=N, N=H, K=2 * H, beta=1.0)
+            self._dgrad(ws.dpq, q + "w_pq", ws.dcat[:, :H], N, ws.amax_dpq[i], accumulate=True)
             if self.ln:
                 ops.layernorm_bwd(ws.dcat[:, :H], ws.h[i], W[q + "ln_g"], ws.ln_mean[i], ws.ln_rstd[i], dh,
                                   G[q + "ln_g"], G[q + "ln_b"], N, H, accumulate_dx=True)

@@ -5,8 +5,15 @@
 timestep  add_noise -> agent forward (activations kept) -> prior forward -> per-crystal loss + KL proxy +
 reward weighting with analytic output gradients (mi_rl_loss) -> hand-written backward into ONE flat fp32
 gradient buffer; every `accum_steps` timesteps one all-reduce of that buffer across ranks (NCCL over
-NVLink; gloo in CPU tests of the host logic) followed by the flat Adam kernel.  A whole timestep is one
-captured CUDA graph (the step index and the schedule scalars live on the device), replayed T times.
+NVLink; gloo in CPU tests of the host logic) followed by the flat Adam kernel.
+
+Timestep grouping.  The reference fine-tunes <= 18 crystals for 3 x 1000 timesteps: one timestep of
+such a batch is ~260 launches of a few microseconds of work each (5.2 ms, launch- and latency-bound).  The weights
+only change every `accum_steps` timesteps, so the timesteps inside one accumulation window are independent: G of
+them are stacked into ONE batch of G x B crystals (each copy with its own time index and noise) and go through one
+forward / backward.  The gradient is the same sum, accumulated in a different order (fp32: ~1e-7 relative); the
+noise is drawn slot by slot in the reference's order.  A whole group is one captured CUDA graph (the time indices
+and schedule scalars live on the device), replayed timesteps / G times.
 
 Sharding: every rank holds the full batch description, owns a contiguous slice of the
 crystals balanced by sum n^2, draws the noise for the GLOBAL batch and slices it (so results do not
@@ -69,8 +76,9 @@ def partition_crystals(num_atoms, world):
 
 class FineTuner:
     def __init__(self, agent, prior, lr, accum_steps, sigma, process_group=None, rank=0, world=1, noise=None,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, group=None):
         self.agent, self.prior = agent, prior
+        self.group = group          # timesteps stacked per launch; None = chosen from the batch's edge count
         self.lr, self.accum, self.sigma = float(lr), int(accum_steps), float(sigma)
         self.pg, self.rank, self.world = process_group, rank, world
         self.noise = noise
@@ -84,6 +92,17 @@ class FineTuner:
         self.adam_t = 0
 
     # ------------------------------------------------------------------ one epoch over one batch
+    # edges per stacked launch the grouping aims for: enough to fill the machine (the per-edge GEMMs switch to their
+    # 128x256 tiles at ~9.3k edges), small enough to keep the training workspace around a GB
+    GROUP_EDGES = 40000
+
+    def group_size(self, edges_local):
+        """largest divisor of accum_steps that keeps a stacked group at <= GROUP_EDGES edges (>= 1)"""
+        want = max(1, min(self.accum, self.GROUP_EDGES // max(1, edges_local)))
+        if self.group is not None:
+            want = max(1, min(self.accum, int(self.group)))
+        return max(d for d in range(1, want + 1) if self.accum % d == 0)
+
     def run_batch(self, batch, timesteps):
         """for t in range(timesteps): ... (pipeline/mat_invent.py:150-170).  Returns the epoch's
         (loss, loss_diff, loss_kl) sums in the reference's normalisation (per-batch, :172-174)."""
@@ -99,55 +118,83 @@ class FineTuner:
         if hi <= lo:
             raise ValueError("rank %d got no crystals: need at least one crystal per rank" % self.rank)
         local = _LocalBatch(agent, batch, lo, hi, n_lo, n_hi)
-        g = local.graph
-        B, N = g.B, g.N
+        B, N = local.graph.B, local.graph.N
         reward = batch.reward.to(dev, torch.float32)[lo:hi].contiguous()
         w_kl = (self.sigma * (1.1 - reward)).contiguous()
         scale = 1.0 / (Bg * self.accum)
         noise = self.noise or TorchNoise(dev)
         in_graph_noise = isinstance(noise, PhiloxNoise)
-        # global noise buffers (every rank draws the whole batch, uses its slice)
-        z_l, z_x, z_a = (torch.empty(Bg, 3, 3, device=dev), torch.empty(Ng, 3, device=dev),
-                         torch.empty(Ng, A, device=dev))
-        zl, zx, za = z_l[lo:hi], z_x[n_lo:n_hi], z_a[n_lo:n_hi]
-        l_t, x_t = torch.empty(B, 3, 3, device=dev), torch.empty(N, 3, device=dev)
-        a_t, tar_x = torch.empty(N, A, device=dev), torch.empty(N, 3, device=dev)
-        temb = torch.empty(B, agent.time_dim, device=dev)
-        loss, kl = torch.empty(B, device=dev), torch.empty(B, device=dev)
-        d = (torch.empty(B, 3, 3, device=dev), torch.empty(N, 3, device=dev), torch.empty(N, A, device=dev))
-        stats = torch.zeros(2, device=dev)
-        t_dev = torch.full((1,), T, dtype=torch.int32, device=dev)
         ttab, ntab = agent.time_table(), agent.noise_table()
-        ws_a, ws_p = dec.workspace(g, True), pdec.workspace(g, False)
         costs = agent._costs()
+        stats = torch.zeros(2, device=dev)
+        G = self.group_size(local.graph.E) if self.use_graph or self.group else 1
+        groups = {}
 
-        def body():
-            ops.sampler_step_begin(t_dev, ttab, temb, B, agent.time_dim)
-            if in_graph_noise:
-                noise.fill(z_l), noise.fill(z_x), noise.fill(z_a)      # draw order :102, :111
-            ops.add_noise(local.L0, local.x0, local.Z, zl, zx, za, B, N, A, ntab, l_t, x_t, a_t, tar_x, t_dev=t_dev)
-            pa = dec.forward_graph(g, temb, a_t, x_t, l_t, train=True, ws=ws_a)
-            pp = pdec.forward_graph(g, temb, a_t, x_t, l_t, train=False, ws=ws_p)
-            ops.rl_loss(pa, (zl, tar_x, za), pp, g.node_off, B, A, costs, reward, w_kl, scale, loss, kl, d, stats)
-            dec.backward_graph(g, temb, a_t, x_t, l_t, d[0], d[1], d[2], ws=ws_a)
-            ops.sampler_step_end(t_dev)
-
-        graph = None
-        for t in range(timesteps):
-            if not in_graph_noise:
-                z_l.copy_(noise.step_randn((Bg, 3, 3)))
-                z_x.copy_(noise.step_randn((Ng, 3)))
-                z_a.copy_(noise.step_randn((Ng, A)))
-            if not self.use_graph or t == 0:
-                body()
+        def make_group(Gn):
+            """buffers + body for Gn stacked timesteps (slot j holds timestep t0 + j)"""
+            g = dec.graph_for(na[lo:hi] * Gn)
+            # global noise per slot (every rank draws the whole batch, uses its slice)
+            z_l, z_x, z_a = (torch.empty(Gn, Bg, 3, 3, device=dev), torch.empty(Gn, Ng, 3, device=dev),
+                             torch.empty(Gn, Ng, A, device=dev))
+            if self.world > 1:      # this rank's crystals of every slot, contiguous (loss targets)
+                zl, zx, za = (torch.empty(Gn, B, 3, 3, device=dev), torch.empty(Gn, N, 3, device=dev),
+                              torch.empty(Gn, N, A, device=dev))
             else:
-                if graph is None:
+                zl, zx, za = z_l, z_x, z_a
+            l_t, x_t = torch.empty(Gn * B, 3, 3, device=dev), torch.empty(Gn * N, 3, device=dev)
+            a_t, tar_x = torch.empty(Gn * N, A, device=dev), torch.empty(Gn * N, 3, device=dev)
+            temb = torch.empty(Gn * B, agent.time_dim, device=dev)
+            loss, kl = torch.empty(Gn * B, device=dev), torch.empty(Gn * B, device=dev)
+            d = (torch.empty(Gn * B, 3, 3, device=dev), torch.empty(Gn * N, 3, device=dev), torch.empty(Gn * N, A, device=dev))
+            t_vec = torch.zeros(Gn, dtype=torch.int32, device=dev)          # time index of every slot
+            rew, wk = reward.repeat(Gn).contiguous(), w_kl.repeat(Gn).contiguous()
+            ws_a, ws_p = dec.workspace(g, True), pdec.workspace(g, False)
+
+            def body():
+                for j in range(Gn):
+                    tj = t_vec[j:j + 1]
+                    ops.sampler_step_begin(tj, ttab, temb[j * B:(j + 1) * B], B, agent.time_dim)
+                    if in_graph_noise:
+                        noise.fill(z_l[j]), noise.fill(z_x[j]), noise.fill(z_a[j])      # draw order :102, :111
+                    if self.world > 1:
+                        zl[j].copy_(z_l[j, lo:hi]), zx[j].copy_(z_x[j, n_lo:n_hi]), za[j].copy_(z_a[j, n_lo:n_hi])
+                    ops.add_noise(local.L0, local.x0, local.Z, zl[j], zx[j], za[j], B, N, A, ntab,
+                                  l_t[j * B:(j + 1) * B], x_t[j * N:(j + 1) * N], a_t[j * N:(j + 1) * N],
+                                  tar_x[j * N:(j + 1) * N], t_dev=tj)
+                pa = dec.forward_graph(g, temb, a_t, x_t, l_t, train=True, ws=ws_a)
+                pp = pdec.forward_graph(g, temb, a_t, x_t, l_t, train=False, ws=ws_p)
+                ops.rl_loss(pa, (zl.view(Gn * B, 3, 3), tar_x, za.view(Gn * N, A)), pp, g.node_off, Gn * B, A, costs, rew, wk,
+                            scale, loss, kl, d, stats)
+                dec.backward_graph(g, temb, a_t, x_t, l_t, d[0], d[1], d[2], ws=ws_a)
+
+            return dict(body=body, z=(z_l, z_x, z_a), t_vec=t_vec, graph=None, runs=0)
+
+        t = 0
+        while t < timesteps:
+            Gn = min(G, self.accum - (t % self.accum), timesteps - t)     # a group never straddles an optimizer step
+            grp = groups.get(Gn)
+            if grp is None:
+                grp = groups[Gn] = make_group(Gn)
+            z_l, z_x, z_a = grp["z"]
+            # time of timestep it: T - it (times = T - t_idx, diffusion.py:86-87)
+            grp["t_vec"].copy_(torch.arange(T - t, T - t - Gn, -1, dtype=torch.int32), non_blocking=False)
+            if not in_graph_noise:
+                for j in range(Gn):
+                    z_l[j].copy_(noise.step_randn((Bg, 3, 3)))
+                    z_x[j].copy_(noise.step_randn((Ng, 3)))
+                    z_a[j].copy_(noise.step_randn((Ng, A)))
+            if not self.use_graph or grp["runs"] == 0:
+                grp["body"]()
+            else:
+                if grp["graph"] is None:
                     torch.cuda.synchronize()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        body()
-                graph.replay()
-            if (t + 1) % self.accum == 0:
+                    grp["graph"] = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(grp["graph"]):
+                        grp["body"]()
+                grp["graph"].replay()
+            grp["runs"] += 1
+            t += Gn
+            if t % self.accum == 0:
                 self.optimizer_step()
         if timesteps % self.accum != 0:
             self.optimizer_step()

@@ -184,10 +184,10 @@ def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, am
     return out
 
 
-def gather_rows_dsilu(dOut, idx, ptr, z, dX, E, H):
-    _f32(dOut), _f32(z), _f32(dX), _i32(idx), _i32(ptr)
+def gather_rows_dsilu(dOut, idx, ptr, z, dX, E, H, amax_out=None):
+    _f32(dOut), _f32(z), _f32(dX), _i32(idx), _i32(ptr), _f32(amax_out)
     check(lib().mi_gather_rows_dsilu(_p(dOut), _ld(dOut), _p(idx), _p(ptr), _p(z), _ld(z) if z is not None else 0,
-                                     _p(dX), _ld(dX), E, H, _stream()), "mi_gather_rows_dsilu")
+                                     _p(dX), _ld(dX), E, H, _p(amax_out), _stream()), "mi_gather_rows_dsilu")
     return dX
 
 
