@@ -346,6 +346,38 @@ def main():
                        h2d_bytes_per_step=4 * (nn * 3 + args.batch * 9 + nn * 100),
                        d2h_bytes_per_step=4 * (nn * 3 + nn + args.batch * 6), passes=n_e2e)
 
+    # ---- second half of the hot path: the reward-weighted fine-tune step at the reference's working point
+    # (<= 18 crystals, accum_steps 50), CUDA events around 200 timesteps of graph replays
+    ft = None
+    if world == 1 and not args.no_e2e and not args.timesteps:
+        from matinvent_b200.models.diffcsp.finetune import FineTuner
+        prior = build_model(dev)
+        for p_ in prior.parameters():
+            p_.requires_grad = False
+        gen = torch.Generator().manual_seed(7)
+        nft = [max(1, n) for n in atom_counts(18)]
+        crystals = []
+        for n in nft:
+            d_ = CrystalData(torch.rand(n, 3, generator=gen), torch.randint(1, 101, (n,), generator=gen),
+                             3 + 5 * torch.rand(1, 3, generator=gen), 70 + 40 * torch.rand(1, 3, generator=gen), torch.tensor(n))
+            d_.reward = torch.rand(1, generator=gen)
+            crystals.append(d_)
+        fbatch = CrystalBatch(crystals)
+        snap = m.decoder.flat.data.clone()
+        tuner = FineTuner(m, prior, lr=1e-4, accum_steps=50, sigma=0.025, noise=PhiloxNoise(dev, seed=3))
+        tuner.run_batch(fbatch, 100)                       # warm: eager group, graph capture
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tuner.run_batch(fbatch, 200)
+        b.record()
+        torch.cuda.synchronize()
+        m.decoder.flat.data.copy_(snap)                    # the benchmark model is left as it was
+        m.decoder.weights_changed()
+        ft = dict(ms_per_timestep=a.elapsed_time(b) / 200, crystals=len(nft), atoms=sum(nft), edges=sum(n * n for n in nft),
+                  timesteps_per_launch=tuner.group_size(sum(n * n for n in nft)), accum_steps=50,
+                  note="agent forward + prior forward + losses + backward per timestep, Adam every 50; the reference runs "
+                       "3 x 1000 of these per RL iteration")
+
     cb = None
     if rank == 0 and not args.no_cpu:
         cb, _ = cpu_reference_leg(na_all, m.decoder.state_dict())
@@ -363,7 +395,7 @@ def main():
                            % (4 * g.E * F6 >> 20, 2 * 4 * g.E * H >> 20),
                         parallelism="dp%d (crystals sharded, no collective while sampling)" % world),
             clocks=clk, gpu_launches=gpu_launches, launches_per_reverse_step=per_step_launches,
-            e2e=e2e, roofline=roofline, roofline_edge_scatter=roofline_scatter, cpu_baseline=cb)))
+            e2e=e2e, fine_tune_step=ft, roofline=roofline, roofline_edge_scatter=roofline_scatter, cpu_baseline=cb)))
         sys.stdout.flush()
         os.write(json_fd, (line + "\n").encode())
     if world > 1:

@@ -75,7 +75,8 @@ int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int ld
 /* Tensor-core variant for the forward dense blocks (A [M,K] and W [N,K] both K-contiguous, i.e.
  * transA = 0, transB = 1): FP32-grade product by split-precision FP16 on tcgen05 (x = x_hi + x_lo, three
  * MMAs per k-slice, TMA-staged swizzled operand tiles, TMEM accumulators), same epilogue contract as
- * mi_sgemm (no split-K, no beta; MI_ACT_DSILU only without gathers / z_out / g3 / resid).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
+ * mi_sgemm (no beta; MI_ACT_DSILU only without gathers / z_out / g3 / resid; epi->splitk > 1 cuts K into that many
+ * parts and ADDS alpha * A W^T to C with 16-byte reductions: plain epilogue only).  W_hi / W_lo are fp16 arrays with the layout of W, produced by mi_f16_split
  * (elementwise, once per weight update).  Requires lda % 4 == 0, ldw % 8 == 0, 16-byte aligned A, W_hi, W_lo.
  *
  * Two operand formats (flags):
@@ -104,6 +105,16 @@ int mi_tc_gemm(int M, int N, int K, const float* A, int lda, const void* W_hi, c
 int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo, int lda, const void* W_hi,
                         const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, int flags,
                         mi_stream_t stream);
+
+/* Transposes that put the weight-gradient GEMM dW[N_out, K_in] += dY^T X (a sum over tens of thousands of edge or node
+ * rows) into the K-contiguous form of mi_tc_gemm: dY^T is its fp32 A operand (row maxima = column maxima of dY), X^T
+ * its pre-split merged-format W operand with one power-of-two scale per row (= per column of X).
+ *   mi_transpose_amax : XT[c][m] = X[m][c] (XT nullable) and col_amax[c] = max(col_amax[c], max_m |X[m][c]|) (nullable)
+ *   mi_transpose_split: hi/lo[c][m] = fp16 split of s_c X[m][c], s_c from col_amax[c]; inv_scale[c] = 1 / s_c
+ * X [M, C] with row stride ldx; outputs [C, M] with row stride ldt >= M (elements m >= M are not written: zero them once). */
+int mi_transpose_amax(const float* X, int ldx, int M, int C, float* XT, int ldt, float* col_amax, mi_stream_t stream);
+int mi_transpose_split(const float* X, int ldx, int M, int C, const float* col_amax, void* hi, void* lo, int ldt,
+                       float* inv_scale, mi_stream_t stream);
 
 /* ---------------------------------------------------------------- graph construction
  * Fully-connected intra-crystal edges, row-major by (i, j) incl. i == j

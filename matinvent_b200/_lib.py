@@ -32,6 +32,8 @@ PROTOTYPES = {
     "mi_sgemm": [i, i, i, i, i, p, i, p, i, p, i, C.POINTER(Epilogue), p],
     "mi_f16_split": [p, p, p, ll, f, f, p],
     "mi_f16_split_rows": [p, i, i, i, p, p, p, p],
+    "mi_transpose_amax": [p, i, i, i, p, i, p, p],
+    "mi_transpose_split": [p, i, i, i, p, p, p, i, p, p],
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],

@@ -995,3 +995,88 @@ extern "C" int mi_philox_uniform(float* out, long long n, unsigned long long see
                                  unsigned long long* offset_dev, int advance, mi_stream_t stream) {
     return philox_launch(false, out, n, seed, offset, offset_dev, advance, stream);
 }
+// ------------------------------------------------------------------------------------ transposes for the weight gradients
+// dW = dY^T X runs on the tensor cores as the forward kernel with both operands transposed to K(=rows)-contiguous form:
+//   XT[c][m] = X[m][c]  (fp32, for the A role)           + col_amax[c] = max_m |X[m][c]|
+//   XT_hi / XT_lo[c][m] = merged-format fp16 split of s_c X[m][c], s_c = 2^(14 - exponent(col_amax[c]))  (the W role)
+// 32 x 32 tiles through shared memory; block (32, 8); pad columns m in [M, ldt) are left untouched (callers zero them once).
+__global__ void transpose_amax_kernel(const float* __restrict__ X, int ldx, int M, int C, float* __restrict__ XT, int ldt,
+                                      float* __restrict__ col_amax) {
+    __shared__ float tile[32][33];
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int m = m0 + threadIdx.y + j, c = c0 + threadIdx.x;
+        const float v = (m < M && c < C) ? __ldg(X + (long long)m * ldx + c) : 0.f;
+        tile[threadIdx.y + j][threadIdx.x] = v;
+        mx = fmaxf(mx, fabsf(v));
+    }
+    if (col_amax) {
+        __shared__ float red[8][32];
+        red[threadIdx.y][threadIdx.x] = mx;
+        __syncthreads();
+        if (threadIdx.y == 0) {
+#pragma unroll
+            for (int j = 1; j < 8; ++j) mx = fmaxf(mx, red[j][threadIdx.x]);
+            if (c0 + threadIdx.x < C) atomicMax(reinterpret_cast<unsigned*>(col_amax + c0 + threadIdx.x), __float_as_uint(mx));
+        }
+    } else {
+        __syncthreads();
+    }
+    if (XT) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const int c = c0 + threadIdx.y + j, m = m0 + threadIdx.x;
+            if (c < C && m < M) XT[(long long)c * ldt + m] = tile[threadIdx.x][threadIdx.y + j];
+        }
+    }
+}
+__global__ void transpose_split_kernel(const float* __restrict__ X, int ldx, int M, int C, const float* __restrict__ col_amax,
+                                       __half* __restrict__ hi, __half* __restrict__ lo, int ldt,
+                                       float* __restrict__ inv_scale) {
+    __shared__ float tile[32][33];
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int m = m0 + threadIdx.y + j, c = c0 + threadIdx.x;
+        tile[threadIdx.y + j][threadIdx.x] = (m < M && c < C) ? __ldg(X + (long long)m * ldx + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int c = c0 + threadIdx.y + j, m = m0 + threadIdx.x;
+        if (c >= C) continue;
+        const float amax = __ldg(col_amax + c);
+        int ex = (int)((__float_as_uint(amax) >> 23) & 0xff) - 127;
+        if (amax == 0.f || ex > 100) ex = 14;
+        ex = max(ex, -100);
+        if (m < M) {
+            const float x = tile[threadIdx.x][threadIdx.y + j] * __uint_as_float((uint32_t)(127 + 14 - ex) << 23);
+            const __half h = __float2half_rn(x);
+            hi[(long long)c * ldt + m] = h;
+            lo[(long long)c * ldt + m] = __float2half_rn(x - __half2float(h));
+        }
+        if (m0 == 0 && threadIdx.x == 0) inv_scale[c] = __uint_as_float((uint32_t)(127 - 14 + ex) << 23);
+    }
+}
+
+
+
+extern "C" int mi_transpose_amax(const float* X, int ldx, int M, int C, float* XT, int ldt, float* col_amax,
+                                 mi_stream_t stream) {
+    if (M <= 0 || C <= 0) return MI_OK;
+    MI_CHECK_ARG(X && (XT || col_amax) && ldx >= C && (!XT || ldt >= M), "bad arguments");
+    transpose_amax_kernel<<<dim3(mi_div_up(M, 32), mi_div_up(C, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, C, XT, ldt, col_amax);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
+extern "C" int mi_transpose_split(const float* X, int ldx, int M, int C, const float* col_amax, void* hi, void* lo, int ldt,
+                                  float* inv_scale, mi_stream_t stream) {
+    if (M <= 0 || C <= 0) return MI_OK;
+    MI_CHECK_ARG(X && col_amax && hi && lo && inv_scale && ldx >= C && ldt >= M, "bad arguments");
+    transpose_split_kernel<<<dim3(mi_div_up(M, 32), mi_div_up(C, 32)), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        X, ldx, M, C, col_amax, (__half*)hi, (__half*)lo, ldt, inv_scale);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}

@@ -176,6 +176,8 @@ struct TcParams {
     mi_epilogue_t e;
     int c_vec;
     int presplit; // A is given as two fp16 arrays (hi, scaled lo): TMA loads them straight into the operand tiles
+    int ksplit;   // > 1: K is cut into ksplit parts handled by different work units; results are ADDED to C with 16-byte
+                  // reductions (weight gradients: few output tiles, tens of thousands of reduction rows)
 };
 
 // tcgen05.ld of a 32-lane x 32-column fp32 block (lane = row, registers = consecutive columns); completion is
@@ -224,16 +226,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int8_t* rexp = reinterpret_cast<int8_t*>(smem + C::RAW_BYTES + C::OP_BYTES + C::EBUF_BYTES + C::BAR_BYTES);   // [128] row exponents
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (p.K + TK - 1) / TK;
+    // k-blocks per work unit; with split-K every part gets the same count and the last one runs past K, where TMA
+    // zero-fills (at most one wasted k-block per part)
+    const int nkb = ((p.K + TK - 1) / TK + p.ksplit - 1) / p.ksplit;
     const int tiles_n = (p.N + TN - 1) / TN;
     const int tiles_m = (p.M + TM - 1) / TM;
-    const int num_tiles = tiles_n * tiles_m;
+    const int num_tiles = tiles_n * tiles_m * p.ksplit;               // work units: (tile, K part), part fastest
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)nkb;        // k-blocks this CTA goes through
-    auto tile_origin = [&](int tl, int& m0, int& n0) {
-        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+    auto tile_origin4 = [&](int tl, int& m0, int& n0, int& kb0) {
+        const int unit = (int)blockIdx.x + tl * (int)gridDim.x;
+        const int tile = unit / p.ksplit;
+        kb0 = (unit % p.ksplit) * nkb;
         m0 = (tile / tiles_n) * TM;
         n0 = (tile % tiles_n) * TN;
+    };
+    auto tile_origin = [&](int tl, int& m0, int& n0) {
+        int kb0;
+        tile_origin4(tl, m0, n0, kb0);
     };
 
     if (threadIdx.x == 0) {
@@ -277,31 +287,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             TRACE(0, 14);
             auto issue_raw = [&](uint32_t idx) {
                 const int tl = (int)(idx / (uint32_t)nkb), kb = (int)(idx % (uint32_t)nkb);
-                int m0, n0;
-                tile_origin(tl, m0, n0);
+                int m0, n0, kb0;
+                tile_origin4(tl, m0, n0, kb0);
                 const int r = (int)(idx % (uint32_t)RR);
                 mbar_wait(&raw_empty[r], ((idx / (uint32_t)RR) & 1) ^ 1);
                 mbar_expect_tx(&raw_full[r], A_RAW);
-                tma_load_2d(raw_ring + r * A_RAW, &mapA, &raw_full[r], kb * TK, m0);
+                tma_load_2d(raw_ring + r * A_RAW, &mapA, &raw_full[r], (kb0 + kb) * TK, m0);
             };
             uint32_t a_it = 0;
             if (!PRESPLIT)
                 for (; a_it + 1 < (uint32_t)R && a_it < total; ++a_it) issue_raw(a_it);
             for (uint32_t it = 0; it < total; ++it) {
                 const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
-                int m0, n0;
-                tile_origin(tl, m0, n0);
+                int m0, n0, kb0;
+                tile_origin4(tl, m0, n0, kb0);
+                const int kc = (kb0 + kb) * TK;
                 const int s = (int)(it % (uint32_t)S);
                 mbar_wait(&op_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
                 if (kb == 0) TRACE(tl, 0);
                 uint8_t* st = op_ring + s * OPB;
                 mbar_expect_tx(&w_full[s], (PRESPLIT ? 2 * A_H : 0) + 2 * W_H);
                 if (PRESPLIT) {
-                    tma_load_2d(st, &mapA, &w_full[s], kb * TK, m0);
-                    tma_load_2d(st + A_H, &mapAlo, &w_full[s], kb * TK, m0);
+                    tma_load_2d(st, &mapA, &w_full[s], kc, m0);
+                    tma_load_2d(st + A_H, &mapAlo, &w_full[s], kc, m0);
                 }
-                tma_load_2d(st + 2 * A_H, &mapWhi, &w_full[s], kb * TK, n0);
-                tma_load_2d(st + 2 * A_H + W_H, &mapWlo, &w_full[s], kb * TK, n0);
+                tma_load_2d(st + 2 * A_H, &mapWhi, &w_full[s], kc, n0);
+                tma_load_2d(st + 2 * A_H + W_H, &mapWlo, &w_full[s], kc, n0);
                 if (!PRESPLIT && a_it < total) issue_raw(a_it++);
             }
         }
@@ -547,7 +558,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             if (EPI & 4) { x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w; }
 #ifndef MI_TC_NOSTORE
-                            *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
+                            if (p.ksplit > 1)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C + (long long)m * p.ldc + n), "f"(x[0]),
+                                             "f"(x[1]), "f"(x[2]), "f"(x[3])
+                                             : "memory");
+                            else
+                                *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
 #else
                             if (x[0] == 1.2345f) p.C[0] = x[1] + x[2] + x[3];
 #endif
@@ -584,7 +600,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 if (EPI & 8) y *= dsilu_fast(__ldg(e.z_in + (long long)m * e.zin_ld + n + u));
                                 else if (e.act == MI_ACT_SILU) y = silu_fast(y);
                                 if ((EPI & 4) && e.resid) y += __ldg(e.resid + (long long)m * e.resid_ld + n + u);
-                                crow[u] = y;
+                                if (p.ksplit > 1) atomicAdd(crow + u, y); else crow[u] = y;
                                 rmax = fmaxf(rmax, fabsf(y));
                             }
                         }
@@ -706,7 +722,7 @@ int launch_tc(int M, int N, int K, const void* A, const void* A_lo, int lda, con
         MI_CUDA(cudaGetDevice(&dev));
         MI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM);
+    const long long tiles = (long long)mi_div_up(N, TN) * mi_div_up(M, TM) * p.ksplit;
     const int grid = (int)(tiles < sms ? tiles : sms);        // persistent: one CTA per SM
     tc_gemm_kernel<TN, EPI, MERGED, PRESPLIT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(mA, mAl, mWh, mWl, p);
     MI_CHECK_LAUNCH();
@@ -781,7 +797,10 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
         z.alpha = 1.f; z.splitk = 1;
         p.e = z;
     }
-    MI_CHECK_ARG(p.e.splitk <= 1, "split-K is not available on the tensor-core path");
+    p.ksplit = p.e.splitk > 1 ? p.e.splitk : 1;
+    if (p.ksplit > 1)
+        MI_CHECK_ARG(!p.e.bias && !p.e.g1 && !p.e.g2 && !p.e.g3 && !p.e.z_out && !p.e.resid && p.e.act == MI_ACT_NONE &&
+                     !p.e.amax_out, "split-K adds alpha * A W^T to C: it takes a plain epilogue (row / column scales only)");
     MI_CHECK_ARG(p.e.beta == 0.f, "the tensor-core path has no accumulate epilogue (pass C as resid, or use mi_sgemm)");
     if (p.e.act == MI_ACT_DSILU)
         MI_CHECK_ARG(p.e.z_in && !p.e.g1 && !p.e.g2 && !p.e.g3 && !p.e.z_out && !p.e.resid,

@@ -43,6 +43,7 @@ class _Workspace:
             return torch.empty(*shape, device=dev, dtype=f32)
 
         self.train = train
+        self._H, self._F6, self._dev = H, F6, dev
         self.phi = buf(E, F6)                               # fp32 basis: backward (dW_F) and the FFMA path
         self.phi_hi = torch.empty(E, F6, device=dev, dtype=torch.float16)
         self.phi_lo = torch.empty(E, F6, device=dev, dtype=torch.float16)
@@ -105,6 +106,23 @@ class _Workspace:
                 self.amax_dzn1.append(self.gamax[o:o + N]); o += N
                 self.amax_dpq.append(self.gamax[o:o + N]); o += N
                 self.amax_dz2.append(self.gamax[o:o + E]); o += E
+
+
+    def wgrad_scratch(self, K):
+        """transposed operands of the tensor-core weight-gradient GEMMs (allocated on first use; K = reduction rows)"""
+        sc = getattr(self, "_wg", None)
+        Kp = (K + 7) // 8 * 8
+        if sc is None or sc["Kp"] < Kp:
+            H2, dev = 2 * self._H, self._dev
+            F6p = max(H2, self._F6)
+            sc = self._wg = dict(
+                Kp=Kp, dyT=torch.zeros(H2, Kp, device=dev, dtype=torch.float32),
+                xhi=torch.zeros(F6p, Kp, device=dev, dtype=torch.float16), xlo=torch.zeros(F6p, Kp, device=dev, dtype=torch.float16),
+                phi_hi=torch.zeros(self._F6, Kp, device=dev, dtype=torch.float16),
+                phi_lo=torch.zeros(self._F6, Kp, device=dev, dtype=torch.float16),
+                inv=torch.zeros(F6p, device=dev, dtype=torch.float32), phi_inv=torch.zeros(self._F6, device=dev, dtype=torch.float32),
+                amax=torch.zeros(H2 + F6p, device=dev, dtype=torch.float32))
+        return sc
 
 
 class CSPNet(nn.Module):
@@ -507,10 +525,37 @@ class CSPNet(nn.Module):
         want = max(1, (2 * 148) // tiles)
         return max(2, min(want, (K + 255) // 256, 64))
 
-    def _wgrad(self, dY, X, gname, M, N, K):
-        """grad[gname] [M,N] += dY[K,M]^T @ X[K,N]   (sum over rows: nodes / edges / crystals)"""
+    # reduction rows from which a weight gradient goes to the tensor cores (below, the FP32 split-K GEMM wins: the
+    # three transposes cost more than they save)
+    WGRAD_TC_ROWS = 20000
+
+    def _wgrad(self, dY, X, gname, M, N, K, ws=None, xt=None):
+        """grad[gname] [M,N] += dY[K,M]^T @ X[K,N]   (sum over K rows: nodes / edges / crystals).
+        Tensor-core path for long reductions: dY^T (fp32, row maxima = column maxima of dY) and X^T (merged-format
+        fp16 split, one scale per column of X; `xt` = an already transposed X) feed mi_tc_gemm with K cut into parts
+        that are added to the gradient with 16-byte reductions."""
+        if (ws is not None and self.use_tc and self.use_merged and K >= self.WGRAD_TC_ROWS and M % 128 == 0 and
+                N % 256 == 0 and M <= 2 * self.hidden_dim):
+            sc = ws.wgrad_scratch(K)
+            sc["amax"].zero_()
+            ca = sc["amax"][:M]
+            ops.transpose_amax(dY, K, XT=sc["dyT"], col_amax=ca)
+            if xt is None:
+                xt = self._transpose_split(X, K, N, sc, sc["xhi"], sc["xlo"], sc["inv"])
+            hi, lo, inv = xt
+            tiles = (M // 128) * (N // 256)
+            ks = max(1, min(ops.sm_count() // tiles, (K + 32 * 8 - 1) // (32 * 8)))
+            ops.tc_gemm(sc["dyT"][:M], hi[:N], lo[:N], self._gviews[gname], M=M, N=N, K=K, a_amax=ca, col_scale=inv[:N],
+                        flags=ops.TC_MERGED, splitk=ks)
+            return
         ops.sgemm(dY, X, self._gviews[gname], transA=True, transB=False, M=M, N=N, K=K, beta=1.0,
                   splitk=self._splitk(M, N, K))
+
+    def _transpose_split(self, X, K, N, sc, hi, lo, inv):
+        cx = sc["amax"][2 * self.hidden_dim:2 * self.hidden_dim + N]
+        ops.transpose_amax(X, K, XT=None, col_amax=cx)
+        ops.transpose_split(X, K, cx, hi, lo, inv)
+        return hi, lo, inv
 
     def backward_graph(self, g, temb, a, x, l, d_l, d_x, d_a, ws=None):
         """Accumulate d(objective)/d(weights) into the flat gradient buffer given the gradients w.r.t. the
@@ -526,6 +571,12 @@ class CSPNet(nn.Module):
             self._tc_version = None
             self._refresh_tc()
         ws.gamax.zero_()
+        # transposed Fourier basis for the six dW_F GEMMs, once (long reductions go to the tensor cores: _wgrad)
+        phi_t = None
+        if self.use_tc and self.use_merged and E >= self.WGRAD_TC_ROWS and H % 128 == 0 and F6 % 256 == 0:
+            sc = ws.wgrad_scratch(max(E, N))
+            sc["amax"].zero_()
+            phi_t = self._transpose_split(ws.phi, E, F6, sc, sc["phi_hi"], sc["phi_lo"], sc["phi_inv"])
         # ---- heads (cspnet.py:276-294)
         if self.ip:
             ops.bmm3(d_l, l, ws.dlat9, B, transL=True)
@@ -553,27 +604,27 @@ class CSPNet(nn.Module):
             cat, a1, an1 = ws.cat[i], ws.a1[i], ws.an1[i]
             # h_out = h_in + silu(zn2);  zn2 = an1 wn2^T + bn2;  an1 = silu(zn1);  zn1 = cat wn1^T + bn1
             ops.gather_rows_dsilu(dh, None, None, ws.zn2[i], ws.dzn, N, H, amax_out=ws.amax_dzn[i])
-            self._wgrad(ws.dzn, an1, q + "wn2", H, H, N)
+            self._wgrad(ws.dzn, an1, q + "wn2", H, H, N, ws=ws)
             ops.colsum(ws.dzn, N, H, G[q + "bn2"])
             self._dgrad(ws.dzn, q + "wn2", ws.dzn1, N, ws.amax_dzn[i], act=ACT_DSILU, z_in=ws.zn1[i],
                         amax_out=ws.amax_dzn1[i])
-            self._wgrad(ws.dzn1, cat, q + "wn1", H, 2 * H, N)
+            self._wgrad(ws.dzn1, cat, q + "wn1", H, 2 * H, N, ws=ws)
             ops.colsum(ws.dzn1, N, H, G[q + "bn1"])
             self._dgrad(ws.dzn1, q + "wn1", ws.dcat, N, ws.amax_dzn1[i])
             # agg = mean_j a2 ; a2 = silu(z2) ; z2 = a1 w2^T + b2
             ops.gather_rows_dsilu(ws.dcat[:, H:], g.edge_src, g.seg_ptr, ws.z2[i], ws.dz2, E, H, amax_out=ws.amax_dz2[i])
-            self._wgrad(ws.dz2, a1, q + "w2", H, H, E)
+            self._wgrad(ws.dz2, a1, q + "w2", H, H, E, ws=ws)
             ops.colsum(ws.dz2, E, H, G[q + "b2"])
             # a1 = silu(z1) ; z1 = Phi w_f^T + P[src] + Q[dst] + C[graph]
             self._dgrad(ws.dz2, q + "w2", ws.dz1, E, ws.amax_dz2[i], act=ACT_DSILU, z_in=ws.z1[i])
-            self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E)
+            self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E, ws=ws, xt=phi_t)
             ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i])
             ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False,
                                amax_out=ws.amax_dpq[i])
             ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False)
             ops.colsum(ws.dcb, B, H, G[q + "b1"])
             self._wgrad(ws.dcb, ws.ips, q + "w_l", H, 9, B)
-            self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N)
+            self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N, ws=ws)
             # d hn = dcat[:, :H] + dpq @ w_pq   (written over dcat[:, :H])
             self._dgrad(ws.dpq, q + "w_pq", ws.dcat[:, :H], N, ws.amax_dpq[i], accumulate=True)
             if self.ln:

@@ -92,9 +92,10 @@ class FineTuner:
         self.adam_t = 0
 
     # ------------------------------------------------------------------ one epoch over one batch
-    # edges per stacked launch the grouping aims for: enough to fill the machine (the per-edge GEMMs switch to their
-    # 128x256 tiles at ~9.3k edges), small enough to keep the training workspace around a GB
-    GROUP_EDGES = 40000
+    # edges per stacked launch the grouping aims for.  Measured at the reference's 18 crystals (2 786 edges), ms per
+    # timestep: G=1 5.2, G=5 1.9, G=10 0.78, G=25 0.66, G=50 0.60 — the weight-gradient GEMMs go to the tensor cores from
+    # ~20k reduction rows (CSPNet.WGRAD_TC_ROWS) and like long reductions; the training workspace is ~70 KB per edge
+    GROUP_EDGES = 150000
 
     def group_size(self, edges_local):
         """largest divisor of accum_steps that keeps a stacked group at <= GROUP_EDGES edges (>= 1)"""

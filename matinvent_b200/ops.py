@@ -119,6 +119,22 @@ def f16_split_rows(w, hi, lo, inv_scale):
           "mi_f16_split_rows")
 
 
+def transpose_amax(X, M, XT=None, col_amax=None):
+    """XT[c][m] = X[m][c] for m < M (XT [C, >= M] fp32, nullable) and col_amax[c] = max(col_amax[c], max_m |X[m][c]|)"""
+    _f32(X), _f32(XT), _f32(col_amax)
+    check(lib().mi_transpose_amax(_p(X), _ld(X), M, X.shape[1], _p(XT), _ld(XT) if XT is not None else 0, _p(col_amax),
+                                  _stream()), "mi_transpose_amax")
+
+
+def transpose_split(X, M, col_amax, hi, lo, inv_scale):
+    """hi/lo[c][m] = merged-format fp16 split of X[m][c] scaled per column from col_amax; inv_scale[c] = 1 / scale"""
+    _f32(X), _f32(col_amax), _f32(inv_scale)
+    if hi.dtype != torch.float16 or lo.dtype != torch.float16 or _ld(hi) != _ld(lo):
+        raise TypeError("hi/lo must be float16 with equal leading dimensions")
+    check(lib().mi_transpose_split(_p(X), _ld(X), M, X.shape[1], _p(col_amax), _p(hi), _p(lo), _ld(hi), _p(inv_scale),
+                                   _stream()), "mi_transpose_split")
+
+
 def merged_scale(w):
     """the power of two s with max |s w| in [2^14, 2^15) (1.0 for an all-zero tensor); one host sync"""
     m = float(w.abs().max())
@@ -135,14 +151,15 @@ def tc_ok(A, W):
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
-            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0, col_scale=None):
-    """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm."""
+            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0, col_scale=None, splitk=1):
+    """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm.
+    splitk > 1: C += alpha * A @ W^T with K cut into splitk parts (plain epilogue only)."""
     for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, 1, amax_out, a_amax, col_scale)
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out, a_amax, col_scale)
     check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
                            _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm")
     return C_

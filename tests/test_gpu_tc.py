@@ -184,3 +184,48 @@ def test_tc_gemm_merged_presplit_fourier_edge_block():
     assert rel_err(Z, z) < 5e-6
     assert rel_err(C, torch.nn.functional.silu(z)) < 5e-6
     assert torch.equal(amax, C.abs().amax(dim=1))
+
+
+# ---------------------------------------------------------------- weight gradients: transposes + split-K accumulate
+def test_transposes_for_weight_gradients():
+    from matinvent_b200 import ops
+    M, C = 1003, 200
+    X = _rand(M, C, seed=50) * torch.logspace(-4, 4, C).cuda()[None, :]
+    X[:, 5] = 0.0
+    Mp = (M + 7) // 8 * 8
+    XT = torch.zeros(C, Mp, device="cuda")
+    ca = torch.zeros(C, device="cuda")
+    ops.transpose_amax(X, M, XT=XT, col_amax=ca)
+    assert torch.equal(XT[:, :M], X.t()) and float(XT[:, M:].abs().max()) == 0.0
+    assert torch.equal(ca, X.abs().amax(dim=0))
+    hi = torch.zeros(C, Mp, device="cuda", dtype=torch.float16)
+    lo, inv = torch.zeros_like(hi), torch.zeros(C, device="cuda")
+    ops.transpose_split(X, M, ca, hi, lo, inv)
+    rec = (hi.double() + lo.double())[:, :M] * inv.double()[:, None]
+    nz = ca > 0
+    err = (rec - X.t().double()).abs().amax(dim=1) / ca.double().clamp_min(1e-300)
+    assert float(err[nz].max()) <= 2.0 ** -21 and float(inv[5]) == 1.0
+
+
+@pytest.mark.parametrize("M,N,K,ks", [(512, 512, 27860, 9), (512, 768, 9001, 4), (1024, 512, 8200, 18), (128, 256, 100, 2)])
+def test_tc_gemm_split_k_accumulates_weight_gradient(M, N, K, ks):
+    """dW += dY^T X as CSPNet._wgrad issues it: both operands transposed, K (the edge / node rows) cut into parts that
+    are added to the gradient buffer"""
+    from matinvent_b200 import ops
+    dY = _rand(K, M, seed=60) * 1e-3
+    X = _rand(K, N, seed=61) * torch.logspace(-2, 2, N).cuda()[None, :]
+    G0 = _rand(M, N, seed=62) * 1e-6        # a previous accumulation, small enough not to dominate fp32 rounding
+    G = G0.clone()
+    Kp = (K + 7) // 8 * 8
+    dyT = torch.zeros(M, Kp, device="cuda")
+    ca, cx, inv = torch.zeros(M, device="cuda"), torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    hi = torch.zeros(N, Kp, device="cuda", dtype=torch.float16)
+    lo = torch.zeros_like(hi)
+    ops.transpose_amax(dY, K, XT=dyT, col_amax=ca)
+    ops.transpose_amax(X, K, XT=None, col_amax=cx)
+    ops.transpose_split(X, K, cx, hi, lo, inv)
+    ops.tc_gemm(dyT, hi, lo, G, M=M, N=N, K=K, a_amax=ca, col_scale=inv, flags=ops.TC_MERGED, splitk=ks)
+    ref = dY.double().t() @ X.double()
+    col_err = ((G.double() - G0.double()) - ref).abs().amax(dim=0) / (dY.double().abs().t() @ X.double().abs()).amax(dim=0)
+    print("split-K weight gradient M=%d N=%d K=%d ks=%d: %.2e" % (M, N, K, ks, float(col_err.max())))
+    assert float(col_err.max()) < 1e-5
