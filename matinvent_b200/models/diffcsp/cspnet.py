@@ -53,7 +53,9 @@ class _Workspace:
         # do not change inside a forward)
         self.cb2 = torch.zeros(net.num_layers, B, 2 * H, device=dev, dtype=f32)
         self.h0 = buf(N, H)
-        self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] * (L + 1)
+        # inference: the embedding output keeps its own buffer (the predictor forward of a reverse step reuses the
+        # corrector's: same atom-type state, time and lattice), the layers update one shared buffer in place
+        self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] + [buf(N, H)] * L
         self.cat = [buf(N, 2 * H) for _ in range(nl)]
         self.pq = buf(N, 2 * H)
         self.a1 = [buf(E, H) for _ in range(nl)]
@@ -441,9 +443,12 @@ class CSPNet(nn.Module):
             self._linear(a1, q + "w2", ws.a2, E, **epi2)
 
     # ------------------------------------------------------------------ forward
-    def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None):
+    def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None, reuse_embedding=False):
         """Score network on a prebuilt graph.  temb [B,T], a [N,A], x [N,3], l [B,3,3] fp32 CUDA.
-        heads = which of (lattice, coord, type) outputs to compute.  Returns views into the workspace."""
+        heads = which of (lattice, coord, type) outputs to compute.  Returns views into the workspace.
+        reuse_embedding: temb, a and l are those of the previous call on this workspace (only x moved, as between the
+        corrector and the predictor of one reverse step): the embedding GEMMs and the per-crystal lattice terms of
+        that call are kept."""
         W, H, F = self._views, self.hidden_dim, self.num_freqs
         N, E, B, L = g.N, g.E, g.B, self.num_layers
         ws = ws or self.workspace(g, train)
@@ -454,20 +459,23 @@ class CSPNet(nn.Module):
             self._refresh_tc()
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
         ws.amax.zero_()
-        # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
-        ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
-        self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
-        self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
-        ops.lattice_ip(l, ws.ips, B)
+        reuse = reuse_embedding and not train
+        if not reuse:
+            # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
+            ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
+            self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
+            self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
+            ops.lattice_ip(l, ws.ips, B)
         presplit, merged = self.edge_mode(E)
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
                          ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
                          op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
         # per-crystal term C_b of the first edge linear, all layers in one launch (the layer blocks of the flat weight
         # buffer are equally spaced)
-        lstride = (self._slices["l1.w_l"][0] - self._slices["l0.w_l"][0]) if L > 1 else 0
-        ops.lattice_linear(l, W["l0.w_l"], W["l0.b1"], ws.cb2[0, :, :H], B, H, n_sets=L, w_stride=lstride,
-                           bias_stride=lstride, out_stride=ws.cb2.stride(0))
+        if not reuse:
+            lstride = (self._slices["l1.w_l"][0] - self._slices["l0.w_l"][0]) if L > 1 else 0
+            ops.lattice_linear(l, W["l0.w_l"], W["l0.b1"], ws.cb2[0, :, :H], B, H, n_sets=L, w_stride=lstride,
+                               bias_stride=lstride, out_stride=ws.cb2.stride(0))
         for i in range(L):
             q = "l%d." % i
             k = i if train else 0

@@ -295,7 +295,7 @@ class _StepState:
         _, px, _ = dec.forward_graph(g, self.temb, self.a, self.x, self.l, heads=(False, True, False), ws=ws)
         ops.reverse_corrector(self.x, px, nz(self.zx_c), self.x_half, N, self.coef, self.t_dev)
         # predictor (diffusion.py:345-351)
-        pl, px, pa = dec.forward_graph(g, self.temb, self.a, self.x_half, self.l, ws=ws)
+        pl, px, pa = dec.forward_graph(g, self.temb, self.a, self.x_half, self.l, ws=ws, reuse_embedding=True)
         ops.reverse_predictor(self.x_half, px, nz(self.zx_p), self.x, N, self.l, pl, nz(self.zl), B, self.a, pa,
                               nz(self.za), A, self.coef, self.t_dev)
         ops.sampler_step_end(self.t_dev)
