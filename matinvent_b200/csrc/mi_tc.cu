@@ -3,24 +3,26 @@
 //   C[M,N] = epilogue( A[M,K] . W[N,K]^T ),  A, W fp32 row-major (K contiguous), fp32 accumulate in TMEM.
 //
 // 1e-4 parity after 2 000 chained score-network evaluations rules out plain TF32/BF16/FP16 inputs, so every
-// operand is split  x = x_hi + 2^-11 x_lo  with x_hi = fp16(x), x_lo = fp16((x - x_hi) * 2^11)  (22+ mantissa
-// bits, residual <= 2^-24 |x|) and the product is formed as  a.w ~= a_hi.w_hi + 2^-11 (a_lo.w_hi + a_hi.w_lo):
-// 3 tcgen05.mma kind::f16 per k-slice of 16.  Same accuracy as the classic 3xTF32 scheme at twice the MMA rate
-// and half the operand bytes (an earlier 3xTF32 version of this kernel measured 2140 cycles per 32-wide k-block,
-// bound by shared-memory bandwidth: git history).  Range: |x| < 65504 (activations and weights of this network
-// are O(1..10); out-of-range inputs must use mi_sgemm).
-//   * W_hi / W_lo are split once per weight update (mi_f16_split) and streamed by TMA (SWIZZLE_64B rows);
-//   * A is streamed by TMA as raw fp32 (SWIZZLE_128B rows) and split into two fp16 tiles in shared memory by the
-//     split warpgroup while earlier stages' MMAs run;
-//   * two accumulators in TMEM: main (a_hi.w_hi) and correction (scaled 2^11): the tensor core truncates when it
-//     adds into the accumulator, so the error grows with the number of accumulating instructions — the small
-//     terms stay out of the main accumulator and are folded in by the epilogue in fp32;
-//   * fused epilogue (bias + up to 3 row gathers + pre-activation store + SiLU + residual), same contract as
-//     mi_sgemm, 8 warps reading TMEM with tcgen05.ld.
+// operand is split into an fp16 head and an fp16 tail (22+ mantissa bits) and the product is formed from three
+// tcgen05.mma kind::f16 per k-slice of 16: a_hi.w_hi + a_lo.w_hi + a_hi.w_lo.  Same accuracy as the classic 3xTF32
+// scheme at twice the MMA rate and half the operand bytes.  Two operand formats (include/matinvent_b200.h):
+//   * two accumulators (main, 2^11-scaled correction), tail scaled by 2^11, 128-wide tiles: the tensor core
+//     truncates when it adds into the accumulator, so the small terms stay out of the main accumulator and are
+//     folded in by the epilogue in fp32 (lowest error);
+//   * "merged": one accumulator, unscaled tail, both operands pre-scaled by powers of two into [2^14, 2^15) — a
+//     128x256 tile then double-buffers in TMEM and moves 1.47x fewer shared-memory bytes per flop.
+// fp32 dynamic range: rows of A are rescaled by the power of two their producer's row maximum calls for (exact) and
+// the result row is scaled back in the epilogue; W rows carry per-row scales undone by epi->col_scale.
+//   * W_hi / W_lo are split once per weight update and streamed by TMA (SWIZZLE_64B rows);
+//   * A is streamed by TMA as raw fp32 (SWIZZLE_128B rows) into its own ring and split into two fp16 tiles of an
+//     operand slot by the split warps, or arrives pre-split from its producer (mi_tc_gemm_presplit);
+//   * fused epilogue (column scales, bias, row gathers, pre-activation store, SiLU or SiLU' of the backward, residual,
+//     row maxima for the next GEMM), same contract as mi_sgemm; epi->splitk > 1 cuts K into parts that are ADDED to C
+//     with 16-byte reductions (weight gradients).
 //
-// Persistent CTA per SM, 128 x TN output tiles (TN in {256 merged, 128, 64}), 16 warps: w0 TMA producer, w1 MMA issuer
-// + TMEM owner, w2..7 operand split, w8..15 epilogue (overlapped with the next tile's main loop: TMEM holds the
-// accumulators of two tiles).  Shared memory: a raw fp32 A ring and an fp16 operand ring (see Cfg).
+// Persistent CTA per SM, 128 x TN output tiles (TN in {256 merged, 128, 64}): w0 TMA producer, w1 MMA issuer + TMEM
+// owner, split warps, epilogue warps (overlapped with the next tile's main loop: TMEM holds the accumulators of two
+// tiles).  What bounds it and what was tried: profiles/r1_tc_trace.md.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -30,7 +32,7 @@
 
 namespace {
 
-constexpr int TM = 128;                              // CTA tile rows; columns TN in {128, 64} (template)
+constexpr int TM = 128;                              // CTA tile rows; columns TN in {256, 128, 64} (template)
 // Warp roles: w0 TMA, w1 MMA, then
 //   A split in the kernel : w2..7 operand split, w8..15 epilogue (16 warps: 128 registers per thread)
 //   A pre-split (PRESPLIT): w2..3 idle, w4..19 epilogue — sixteen epilogue warps, because that kernel's epilogue carries the
