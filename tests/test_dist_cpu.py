@@ -89,3 +89,20 @@ def test_sharded_gradient_equals_global_gradient_gloo():
         p.join(300)
         assert p.exitcode == 0
     assert ret["err"] < 1e-5, ret["err"]
+
+
+def test_fine_tune_group_size_divides_the_accumulation_window():
+    """host logic of the stacked-timestep fine-tune step: the group is a divisor of accum_steps (a group never
+    straddles an optimizer step) bounded by the edge budget; an explicit group is clamped the same way"""
+    import types
+    from matinvent_b200.models.diffcsp.finetune import FineTuner
+    f = lambda accum, edges, group=None: FineTuner.group_size(
+        types.SimpleNamespace(accum=accum, group=group, GROUP_EDGES=FineTuner.GROUP_EDGES), edges)
+    assert f(50, 2786) == 50                       # the reference's working point: 18 crystals, whole window in one launch
+    assert f(50, 40000) == 2 and f(50, 200000) == 1
+    assert f(50, 2786, group=10) == 10 and f(50, 2786, group=7) == 5 and f(50, 2786, group=1000) == 50
+    assert f(7, 100) == 7 and f(7, 30000) == 1     # prime window: all or one
+    for accum in (1, 10, 48, 50):
+        for edges in (1, 500, 5000, 60000):
+            g = f(accum, edges)
+            assert accum % g == 0 and (g == 1 or g * edges <= FineTuner.GROUP_EDGES)
