@@ -534,8 +534,8 @@ class CSPNet(nn.Module):
         return max(2, min(want, (K + 255) // 256, 64))
 
     # reduction rows from which a weight gradient goes to the tensor cores (below, the FP32 split-K GEMM wins: the
-    # three transposes cost more than they save)
-    WGRAD_TC_ROWS = 20000
+    # three transposes cost more than they save); MI_WGRAD_TC_ROWS overrides it for tuning runs
+    WGRAD_TC_ROWS = int(os.environ.get("MI_WGRAD_TC_ROWS", "20000"))
 
     def _wgrad(self, dY, X, gname, M, N, K, ws=None, xt=None):
         """grad[gname] [M,N] += dY[K,M]^T @ X[K,N]   (sum over K rows: nodes / edges / crystals).
