@@ -42,6 +42,25 @@ def gold_rg():
     return load_gold("radius_graph.pt")
 
 
+@pytest.fixture(scope="session")
+def gold_baseline():
+    """one forward of the unmodified reference on the benchmark batch (oracle/make_golden.py --baseline)"""
+    return load_gold("baseline_forward.pt")
+
+
+def baseline_inputs(gb):
+    """the inputs oracle/make_golden.py forward_case drew for that fixture, regenerated from its seed"""
+    from oracle import diffcsp_oracle as O
+    na = gb["num_atoms"]
+    B, N = len(na), int(na.sum())
+    g = torch.Generator().manual_seed(gb["seed"])
+    t = O.time_embedding(torch.full((B,), gb["t_int"]), gb["hp"]["time_dim"])
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g)
+    return na, t, a, x, l, torch.repeat_interleave(torch.arange(B), na)
+
+
 def build_module(hp, sd, sigmas_norm, device="cuda"):
     """matinvent_b200 DiffCSPModule from an oracle-style hparam dict + reference-named decoder weights."""
     from matinvent_b200.models.diffcsp import DiffCSPModule

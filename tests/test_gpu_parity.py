@@ -327,6 +327,20 @@ def test_forward_baseline_batch_vs_oracle(gold_full):
     assert max(errs) < 2e-5, errs
 
 
+def test_forward_baseline_batch_vs_reference_golden(gold_full, gold_baseline):
+    """the same size against the UNMODIFIED reference: tests/golden/baseline_forward.pt (oracle/make_golden.py --baseline)"""
+    from conftest import baseline_inputs
+    m = _full_module(gold_full)
+    na, t, a, x, l, n2g = baseline_inputs(gold_baseline)
+    assert m.decoder.edge_mode(int((na * na).sum())) == (True, True)
+    with torch.no_grad():
+        pl, px, pt = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+    gb = gold_baseline
+    errs = (rel_err(pl, gb["ref_pred_l"]), rel_err(px, gb["ref_pred_x"]), rel_err(pt[::8], gb["ref_pred_t_rows8"]))
+    print("baseline-batch forward vs reference golden: lattice %.2e coord %.2e type %.2e" % errs)
+    assert max(errs) < 2e-5, errs
+
+
 def test_gradients_baseline_batch_merged_vs_ffma(gold_full):
     """training forward (pre-activation stores) + hand-written backward at the benchmark's batch: tensor-core
     (merged tiles) against the FP32 CUDA-core path"""

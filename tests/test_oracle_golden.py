@@ -44,6 +44,22 @@ def test_forward_fc_bit_exact(gold_small):
     assert torch.equal(e.int(), c["ref_edges"]) and torch.equal(fd, c["ref_frac_diff"])
 
 
+def test_forward_baseline_batch(gold_baseline):
+    """the oracle against the unmodified reference on the benchmark batch (256 mp_20 crystals, 34 445 edges, full-size
+    net regenerated from its seed and pinned by checksums)"""
+    from conftest import baseline_inputs
+    gb = gold_baseline
+    sd = O.init_params(gb["hp"], gb["seed_weights"])
+    for k, v in sd.items():
+        assert abs(float(v.double().abs().sum()) - gb["checksums"][k]) <= 1e-9 * max(1.0, gb["checksums"][k]), k
+    na, t, a, x, l, n2g = baseline_inputs(gb)
+    assert int((na * na).sum()) == gb["edges"] == 34445
+    with torch.no_grad():
+        pl, px, pt = O.cspnet_forward(sd, gb["hp"], t, a, x, l, na, n2g)
+    for mine, ref in ((pl, gb["ref_pred_l"]), (px, gb["ref_pred_x"]), (pt[::8], gb["ref_pred_t_rows8"])):
+        assert float((mine - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+
+
 def test_forward_knn(gold_small):
     gs = gold_small
     c = gs["forward_knn"]
