@@ -118,7 +118,7 @@ def baseline_forward():
     import numpy as np
     hp = O.default_hparams()
     sn = torch.load(os.path.join(GOLD, "sigmas_norm_T1000.pt"))["sigmas_norm"]
-    ref, _, sd, _ = build(hp, sigmas_norm=sn)
+    ref, prior, sd, sdp = build(hp, sigmas_norm=sn)
     # models/diffcsp/sample.py ATOM_DIST['mp_20'] of the reference (number-of-atoms prior), bench.py's draw
     # (read as a literal from the source: importing that module pulls in pymatgen)
     import ast
@@ -132,6 +132,16 @@ def baseline_forward():
     gold = dict(hp=hp, seed_weights=0, checksums=checksums(sd), num_atoms=c["num_atoms"], seed=101, t_int=650,
                 ref_pred_l=c["ref_pred_l"], ref_pred_x=c["ref_pred_x"], ref_pred_t_rows8=c["ref_pred_t"][::8].clone(),
                 edges=int((c["num_atoms"] ** 2).sum()), seconds=time.time() - t0)
+    # one fine-tune timestep of the same batch (reward-weighted loss + KL proxy, all gradients by the reference's
+    # autograd): the long reductions of the weight gradients are what the CUDA path moves to the tensor cores
+    t1 = time.time()
+    ft, grads = ft_case(hp, ref, prior, [max(1, n) for n in num_atoms], 300)
+    keep = ("crystals", "num_atoms", "t_idx", "sigma", "accum", "noise_seed", "ref_sample_loss", "ref_kl", "ref_loss")
+    gold["ft"] = {k: ft[k] for k in keep}
+    gold["ft_grad_checks"] = {k: dict(abs_sum=float(v.double().abs().sum()), head=v.reshape(-1)[:64].clone())
+                              for k, v in grads.items()}
+    gold["checksums_prior"] = checksums(sdp)
+    gold["ft_seconds"] = time.time() - t1
     torch.save(gold, os.path.join(GOLD, "baseline_forward.pt"))
     print("baseline_forward.pt written: %d atoms, %d edges, reference forward %.1f s" %
           (int(c["num_atoms"].sum()), gold["edges"], gold["seconds"]))

@@ -341,6 +341,36 @@ def test_forward_baseline_batch_vs_reference_golden(gold_full, gold_baseline):
     assert max(errs) < 2e-5, errs
 
 
+def test_ft_gradients_baseline_batch_vs_reference_golden(gold_full, gold_baseline):
+    """one fine-tune timestep of the 256-crystal batch (reward-weighted loss + KL proxy) against the gradients of the
+    UNMODIFIED reference's autograd: at this size the input- and weight-gradient GEMMs of the per-edge blocks run on
+    the tensor cores (transposed operands, split-K accumulate)"""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    ft = gold_baseline["ft"]
+    agent, prior = _full_module(gold_full, 0), _full_module(gold_full, 1)
+    for p in prior.parameters():
+        p.requires_grad = False
+    assert int((ft["num_atoms"] ** 2).sum()) >= agent.decoder.WGRAD_TC_ROWS
+    batch = make_batch(ft["num_atoms"].tolist(), **ft["crystals"])
+    batch.reward = batch.reward.cuda()
+    noised = agent.add_noise(batch, ft["t_idx"], noise=TapeNoise("cuda", seed=ft["noise_seed"]))
+    sample_loss, agent_pred = agent.calc_sample_loss(noised)
+    _, prior_pred = prior.calc_sample_loss(noised)
+    kl = agent.calc_kl_reg(agent_pred, prior_pred, batch)
+    ((batch.reward * sample_loss + kl * (1.1 - batch.reward) * ft["sigma"]).mean() / ft["accum"]).backward()
+    assert rel_err(sample_loss, ft["ref_sample_loss"]) < 1e-4 and rel_err(kl, ft["ref_kl"]) < 1e-4
+    grads = agent.decoder.reference_named_grads()
+    worst = 0.0
+    for k, chk in gold_baseline["ft_grad_checks"].items():
+        g = grads[k].cpu()
+        assert abs(float(g.double().abs().sum()) - chk["abs_sum"]) < 1e-4 * chk["abs_sum"] + 1e-12, k
+        scale = float(g.abs().max()) + 1e-30
+        worst = max(worst, float((g.reshape(-1)[:64] - chk["head"]).abs().max()) / scale)
+        assert float((g.reshape(-1)[:64] - chk["head"]).abs().max()) < 1e-4 * scale, k
+    print("baseline-batch fine-tune gradients vs reference golden: worst head error %.2e of the tensor's max" % worst)
+
+
 def test_gradients_baseline_batch_merged_vs_ffma(gold_full):
     """training forward (pre-activation stores) + hand-written backward at the benchmark's batch: tensor-core
     (merged tiles) against the FP32 CUDA-core path"""
