@@ -199,7 +199,7 @@ def main():
 
     from matinvent_b200 import _lib
     from matinvent_b200.models.diffcsp import DiffCSPSampler, PhiloxNoise
-    from matinvent_b200.models.diffcsp.sample import CrystalBatch, CrystalData, postprocess
+    from matinvent_b200.models.diffcsp.sample import CrystalBatch, CrystalData
     from matinvent_b200 import ops
 
     m = build_model(dev)

@@ -17,7 +17,6 @@ import torch.nn as nn
 
 from ... import ops
 from .cspnet import CSPNet, MAX_ATOMIC_NUM
-from .graph import CrystalGraph
 from .scheduler import BetaScheduler, SigmaScheduler, StepCoefficients, time_embedding_table
 
 

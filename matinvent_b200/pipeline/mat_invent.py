@@ -10,7 +10,6 @@ import os
 import time
 
 import numpy as np
-import torch
 
 from ..models.diffcsp.finetune import FineTuner
 from .base import ReinL
