@@ -324,17 +324,27 @@ def main():
     e2e = None
     if not args.no_e2e:
         sampler = DiffCSPSampler(batch_size=args.batch, num_batches=1)
-        np.random.seed(1234 + rank)
         torch.manual_seed(1234 + rank)
+
+        def same_workload():
+            # generate() draws its atom counts from numpy's global RNG (sample.py:117-138): position the stream so that
+            # it draws exactly this rank's slice of the benchmark workload (atom_counts), i.e. the batch `value` ran
+            from matinvent_b200.models.diffcsp.sample import ATOM_DIST
+            np.random.seed(0)
+            if rank:
+                np.random.choice(21, rank * args.batch, p=ATOM_DIST["mp_20"])
+
         if args.timesteps:
             e2e = None
         else:
-            sampler.generate(m)                         # warm (graph capture for the new atom counts)
+            same_workload()
+            sampler.generate(m)                         # warm
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             n_e2e = max(1, min(args.steps, 2))
             for _ in range(n_e2e):
+                same_workload()
                 data, _ = sampler.generate(m)
             b.record()
             barrier()
@@ -342,6 +352,7 @@ def main():
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             nn = sum(int(d.num_atoms) for d in data)
+            assert nn == g.N, "the end-to-end passes must run the benchmark workload"
             e2e = dict(value=args.batch * world * n_e2e / (float(t) / 1e3), unit="crystals/s",
                        h2d_bytes_per_step=4 * (nn * 3 + args.batch * 9 + nn * 100),
                        d2h_bytes_per_step=4 * (nn * 3 + nn + args.batch * 6), passes=n_e2e)
