@@ -298,7 +298,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             };
             uint32_t a_it = 0;
             if (!PRESPLIT)
-                for (; a_it + 1 < (uint32_t)R && a_it < total; ++a_it) issue_raw(a_it);
+                for (; (int)a_it < R - 1 && a_it < total; ++a_it) issue_raw(a_it);
             for (uint32_t it = 0; it < total; ++it) {
                 const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
                 int m0, n0, kb0;
