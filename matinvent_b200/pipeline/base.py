@@ -1,13 +1,16 @@
 """RL pipeline base — mirror of pipeline/base.py:26-142 (`ReinL`): same constructor arguments, same config
-merge (suite config overridden by pipeline config, :53-59), same `reward_step`.  The long-term memory, loggers
-and reward calculators of the reference are host-side bookkeeping / external property oracles (SURVEY.md §2
-#15-19, out of scope): they are duck-typed here — pass the reference's objects or any stand-in."""
+merge (suite config overridden by pipeline config, :53-59), same `reward_step`.  The long-term memory is the
+device-resident `memory.ltm.LongTimeMem` (pipeline/base.py:64 creates one unconditionally; here `ltm=True` does, and
+any object with the same methods is accepted); loggers and reward calculators of the reference are host-side
+bookkeeping / external property oracles (out of scope): duck-typed — pass the reference's
+objects or any stand-in."""
 import logging
 import os
 
 import numpy as np
 
 from ..config import Config
+from ..memory.ltm import LongTimeMem
 from ..memory.replay_buffer import ReplayBuffer
 from ..models.suite.base import get_device
 
@@ -28,7 +31,7 @@ class ReinL:
         self.sample_cfg = Config.merge(model_suite.sample_cfg, sample_cfg)
         self.finetune_cfg = Config.merge(model_suite.finetune_cfg, finetune_cfg)
         self.sampler = model_suite.get_sampler()
-        self.ltm = ltm
+        self.ltm = LongTimeMem(device=self.device) if ltm is True else ltm
         self.models_dir = os.path.join(save_dir, "models")
         self.sample_dir = os.path.join(save_dir, "samples")
         os.makedirs(self.models_dir, exist_ok=True)

@@ -3,8 +3,9 @@ device (`ft_step`, :125-189 -> models/diffcsp/finetune.FineTuner) and one-proces
 every rank runs the same loop with the same seeds, samples its shard of the crystal batch (no collective),
 all-gathers the sampled crystals for scoring, and fine-tunes with one gradient all-reduce per Adam step.
 
-Validity / SUN filters, extxyz dumps, the long-term memory and its diversity filter are the reference's
-host-side subsystems (out of scope): hooks are called when such objects are supplied."""
+The long-term memory and its diversity filter run on the device (memory/ltm.py, `ltm=True`).  Validity / SUN
+filters and extxyz dumps are the reference's host-side subsystems (out of scope): hooks are called
+when such objects are supplied."""
 import logging
 import os
 import time
@@ -92,11 +93,16 @@ class MatInvent(ReinL):
                                                                           "step_%04d" % self.step)
         log = {"reward mean": float(rewards.mean()), "reward std": float(rewards.std()), "cost": self.cost}
         penalty_strucs = []
-        if self.ltm is not None:
+        if self.ltm is not None:          # pipeline/mat_invent.py:209-237
             self.ltm.extend(sample_struc, rewards, self.step)
+            if hasattr(self.ltm, "calc_metrics"):
+                burden, div_ratio = self.ltm.calc_metrics(getattr(self.reward, "threshold", 0.0))
+                log.update({"crystal_num": len(self.ltm), "unique_comps": len(self.ltm.unique_comps), "burden": burden,
+                            "div_ratio": div_ratio})
             if self.div_filter:
-                rewards, penalty_idx, _, _ = self.ltm.div_filter(sample_struc, rewards, **self.df_args)
+                rewards, penalty_idx, tol_n, buff_n = self.ltm.div_filter(sample_struc, rewards, **self.df_args)
                 penalty_strucs = [sample_struc[p] for p in penalty_idx]
+                logging.info("Diversity filter: tol_n=%d, buff_n=%d", tol_n, buff_n)
         if self.logger is not None:
             self.logger.log(log, step=self.step)
         order = np.argsort(rewards)[::-1]

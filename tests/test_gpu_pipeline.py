@@ -200,3 +200,41 @@ def test_two_gpu_ft_and_sampling_match_single_gpu(tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DIST_CHECK_OK" in out.stdout
+
+
+def test_long_term_memory_keys_and_filter_on_device():
+    """memory/ltm.py:30-109 through the public API: composition / element-set keys from the device kernel partition the
+    crystals like pymatgen's reduced formula / element tuple would; the occurrence penalty follows the reference rule"""
+    from matinvent_b200.memory import LongTimeMem
+    from matinvent_b200.models.diffcsp.sample import CrystalData
+    from oracle.ltm_oracle import LongTimeMemOracle
+    import math
+    from collections import Counter
+
+    def crystal(z):
+        n = len(z)
+        return CrystalData(torch.rand(n, 3), torch.tensor(z), torch.ones(1, 3), torch.full((1, 3), 90.0), torch.tensor(n))
+
+    def formula(z):          # what reduced_formula / the element tuple are keyed on
+        c = Counter(z)
+        g = 0
+        for v in c.values():
+            g = math.gcd(g, v)
+        return tuple(sorted((e, v // g) for e, v in c.items())), tuple(sorted(c))
+
+    rng = np.random.default_rng(3)
+    mine, ref = LongTimeMem(device="cuda"), LongTimeMemOracle()
+    pool = [[8, 8, 22], [22, 8, 8, 8, 8, 22], [26, 8], [8, 26, 26, 8], [3, 15, 8, 8, 8, 8], [8, 22], [22, 8, 8, 8]]
+    for step in range(6):
+        zs = [pool[i] for i in rng.integers(0, len(pool), 40)]
+        rew = rng.random(40)
+        mine.extend([crystal(z) for z in zs], rew, step)
+        f = [formula(z) for z in zs]
+        ref.extend([a for a, _ in f], [b for _, b in f], rew, step)
+        for method in ("composition", "element_comb"):
+            got = mine.div_filter([crystal(z) for z in pool], np.ones(len(pool)), tol=10, buff=20, method=method)
+            want = ref.div_filter([formula(z)[0 if method == "composition" else 1] for z in pool], np.ones(len(pool)),
+                                  tol=10, buff=20, method=method)
+            assert np.allclose(got[0], want[0]) and got[1] == want[1] and got[2:] == want[2:], (step, method)
+        assert mine.unique_comps.numel() == len(ref.unique_comps)
+    assert abs(mine.get_baseline(5) - ref.get_baseline(5)) < 1e-12
