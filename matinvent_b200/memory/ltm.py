@@ -76,8 +76,8 @@ class LongTimeMem:
         occ = torch.searchsorted(srt, keys, right=True) - torch.searchsorted(srt, keys, right=False)
         soft = (occ > tol) & (occ < buff)
         hard = occ >= buff
-        scale = torch.where(soft, (buff - occ).double() / float(buff - tol), torch.ones_like(r))
-        new = torch.where(hard, torch.zeros_like(r), r * scale)
+        ramp = r * (buff - occ).double() / float(buff - tol)          # the reference's order: multiply, then divide
+        new = torch.where(hard, torch.zeros_like(r), torch.where(soft, ramp, r))
         penalty_idx = torch.nonzero(hard).reshape(-1).tolist()
         return new.cpu().numpy(), penalty_idx, int(soft.sum()), int(hard.sum())
 

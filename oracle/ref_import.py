@@ -81,3 +81,20 @@ def make_batch(num_atoms, **extra):
     for k, v in extra.items():
         setattr(b, k, v)
     return b
+
+
+def import_reference_ltm():
+    """The reference's `memory.ltm.LongTimeMem`, unmodified (pandas is installed; its pymatgen / PyG imports are type
+    hints, stubbed under oracle/shims)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    for p in (REF_ROOT, _SHIMS):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, _SHIMS)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_memory_ltm", os.path.join(REF_ROOT, "memory", "ltm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.LongTimeMem

@@ -1,4 +1,4 @@
-"""CPU: the long-term memory's bookkeeping (diversity filter, burden / diversity metrics, baseline) against a pandas
+"""CPU: the long-term memory's bookkeeping (diversity filter, burden / diversity metrics, baseline) against the CPU
 restatement of memory/ltm.py on the same key streams (oracle/ltm_oracle.py).  The keys themselves come from the device
 kernel in the GPU test; here integer keys stand in for the formulas."""
 import numpy as np
@@ -27,7 +27,7 @@ def test_div_filter_and_metrics_match_reference_bookkeeping(method):
         got = mine.div_filter_keys(torch.as_tensor(qc if method == "composition" else qe), qr, tol=10, buff=20, method=method)
         want = ref.div_filter(["c%d" % c for c in qc] if method == "composition" else [("e", int(e)) for e in qe], qr,
                               tol=10, buff=20, method=method)
-        assert np.allclose(got[0], want[0], rtol=0, atol=1e-15) and got[1] == want[1] and got[2:] == want[2:]
+        assert np.array_equal(got[0], want[0]) and got[1] == want[1] and got[2:] == want[2:]
         assert len(mine) == len(ref.memory) and mine.unique_comps.numel() == len(ref.unique_comps)
         for thred, cand in ((0.5, 10), (0.9, 100), (0.99, 30)):
             b1, d1 = mine.calc_metrics(thred, budget=1500, num_candidate=cand)
@@ -36,9 +36,7 @@ def test_div_filter_and_metrics_match_reference_bookkeeping(method):
             assert (d1 is None) == (d2 is None) and (d1 is None or abs(d1 - d2) < 1e-12)
         assert abs(mine.get_baseline(step) - ref.get_baseline(step)) < 1e-12
     # best crystal of every composition (ltm.py:139-149)
-    idx = mine.deduplicate_indices().tolist()
-    df = ref.memory.reset_index(drop=True).sort_values("reward", ascending=False).drop_duplicates(subset=["comp"])
-    assert sorted(idx) == sorted(df.index.tolist())
+    assert sorted(mine.deduplicate_indices().tolist()) == ref.best_row_per_comp()
 
 
 def test_empty_memory_and_empty_query():

@@ -44,3 +44,39 @@ def test_sampler_matches_live_reference_bit_exact():
         mine = O.sample(sd, hp, sch, na, O.Noise(torch.Generator().manual_seed(9)), step_lr=5e-6)
     for k in ("frac_coords", "lattices", "atom_types"):
         assert torch.equal(mine[k], out[k]), k
+
+
+def test_long_term_memory_oracle_matches_live_reference():
+    """oracle/ltm_oracle.py against the UNMODIFIED memory/ltm.py (pandas) driven with duck-typed structures"""
+    import types
+    import warnings
+    import numpy as np
+    from oracle.ltm_oracle import LongTimeMemOracle
+    RefLTM = R.import_reference_ltm()
+
+    def struc(formula, elements):
+        return types.SimpleNamespace(composition=types.SimpleNamespace(reduced_formula=formula), species=list(elements))
+
+    rng = np.random.default_rng(11)
+    names = [("TiO2", ("Ti", "O")), ("FeO", ("Fe", "O")), ("Fe2O3", ("Fe", "O")), ("LiPO4", ("Li", "P", "O")), ("TiO", ("Ti", "O")),
+             ("NaCl", ("Na", "Cl"))]
+    ref, ora = RefLTM(), LongTimeMemOracle()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                  # pandas concat-with-empty FutureWarning inside the reference
+        for step in range(8):
+            pick = [names[i] for i in rng.integers(0, len(names), 30)]
+            rew = rng.random(30)
+            ref.extend([struc(f, e) for f, e in pick], rew, step)
+            ora.extend([f for f, _ in pick], [tuple(sorted(set(e))) for _, e in pick], rew, step)
+            q = [names[i] for i in rng.integers(0, len(names), 12)] + [("KBr", ("K", "Br"))]
+            qr = rng.random(len(q))
+            for method in ("composition", "element_comb"):
+                a = ref.div_filter([struc(f, e) for f, e in q], qr, tol=10, buff=20, method=method)
+                vals = [f for f, _ in q] if method == "composition" else [tuple(sorted(set(e))) for _, e in q]
+                b = ora.div_filter(vals, qr, tol=10, buff=20, method=method)
+                assert np.array_equal(a[0], b[0]) and list(a[1]) == b[1] and (a[2], a[3]) == (b[2], b[3])
+            for thred, cand in ((0.5, 3), (0.95, 100)):
+                m1, m2 = ref.calc_metrics(thred, budget=150, num_candidate=cand), ora.calc_metrics(thred, budget=150, num_candidate=cand)
+                assert m1 == m2, (m1, m2)
+            assert abs(ref.get_baseline(step) - ora.get_baseline(step)) < 1e-15
+            assert len(ref) == len(ora.memory) and len(ref.unique_comps) == len(ora.unique_comps)
