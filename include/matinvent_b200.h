@@ -268,13 +268,37 @@ int mi_build_dst_csr(const int* seg_ptr, const int* edge_dst, int N, int E_cap, 
  * memory/replay_buffer.py:32-73 on padded SoA rows: given keys (64-bit reduced-composition hash) and
  * rewards of `n` candidate rows (old rows first), compute the kept row order:
  * sort by reward desc (stable), drop later duplicates of a key, keep the first `buffer_size`, keep
- * reward > cutoff.  out_idx [n] (first *out_count entries valid). Single CTA (n <= 16384). */
-int mi_replay_select(const unsigned long long* keys, const float* rewards, int n, int buffer_size,
-                     float cutoff, int* out_idx, int* out_count, mi_stream_t stream);
+ * reward > cutoff.  Rewards are float64 like the reference's pandas column.  out_idx [n] (first *out_count entries
+ * valid).  Single CTA: n <= 16384 candidate rows (buffer + one iteration's top-k; the caller pre-selects above that).
+ * Rows are identified by the 64-bit key alone (no collision check: 2^-64 per pair). */
+int mi_replay_select(const unsigned long long* keys, const double* rewards, int n, int buffer_size,
+                     double cutoff, int* out_idx, int* out_count, mi_stream_t stream);
 /* key[b] = hash of the gcd-reduced element-count vector of crystal b (Z in 1..100)
  * (pymatgen reduced_formula equivalence class, memory/replay_buffer.py:38) */
 int mi_composition_key(const int* Z, const int* node_off, int B, unsigned long long* keys,
                        mi_stream_t stream);
+
+/* ---------------------------------------------------------------- post-sampling pipeline
+ * Validity pre-filter of sampled crystals, one warp per crystal; replaces the per-structure Python / mp.Pool loop of
+ * pipeline/filters/opt_filter.py:38-63 (`invalid_filter`).  frac [N,3], L [B,3,3] (rows = lattice vectors),
+ * lengths [B,3], node_off [B+1].  mask[b] bit 0 = max(a,b,c) < max_len (the in-tree rule, opt_filter.py:53-55);
+ * bit 1 = min periodic interatomic distance (27 images) >= min_dist, |det L| >= min_vol, max(a,b,c) <= hard_len
+ * (mattergen `structure_validity`, opt_filter.py:51: un-vendored, restated from its published definition —
+ * parity unpinned).  dmin (nullable, [B]) receives the minimum distance. */
+int mi_validity_prefilter(const float* frac, const float* L, const float* lengths, const int* node_off, int B,
+                          float max_len, float min_dist, float min_vol, float hard_len, int* mask, float* dmin,
+                          mi_stream_t stream);
+/* Composition-level rewards, one warp per crystal: prop[p][b] = sum_el w_el * tables[p][el] with w = mass fraction
+ * (modes[p] = 0) or atomic fraction (1) — the form of rewards/calculators/pymatgen/calc.py:24-45,57-92 (hhi, price,
+ * crustal abundance); NaN table entry of a present element => failed sample (calc.py:63-70).  Then
+ * rewards/reward.py:51-115 in float64: nan_to_num, linear_scaling (targets[p] = 0 ascending, 1 descending, 2 target
+ * value tval[p]; minv/maxv), reduce (0 mean, 1 min, 2 weighted sum), failed -> reward 0.
+ * Z [N] (1..100), node_off [B+1], tables [P,128] and mass [128] device doubles indexed by atomic number; the
+ * per-property configuration arrays are HOST arrays of length P (<= 8).  Out: props [P,B], rewards [B], failed [B]. */
+int mi_composition_reward(const int* Z, const int* node_off, int B, const double* tables, const double* mass, int P,
+                          const int* modes, const int* targets, const double* minv, const double* maxv,
+                          const double* tval, const double* weight, int reduce, double* props, double* rewards,
+                          int* failed, mi_stream_t stream);
 
 #ifdef __cplusplus
 }

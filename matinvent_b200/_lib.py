@@ -62,8 +62,11 @@ PROTOTYPES = {
     "mi_radius_graph_pbc": [p, p, p, i, i, i, i, i, p, p, p, p, p],
     "mi_compact_edges": [p, i, i, p, p, p, p, p, p, p, p, i, p],
     "mi_build_dst_csr": [p, p, i, i, p, p, p, p],
-    "mi_replay_select": [p, p, i, i, f, p, p, p],
+    "mi_replay_select": [p, p, i, i, d, p, p, p],
     "mi_composition_key": [p, p, i, p, p],
+    "mi_validity_prefilter": [p, p, p, p, i, f, f, f, f, p, p, p],
+    "mi_composition_reward": [p, p, i, p, p, i, C.POINTER(i), C.POINTER(i), C.POINTER(d), C.POINTER(d), C.POINTER(d),
+                              C.POINTER(d), i, p, p, p, p],
 }
 
 _lib = None

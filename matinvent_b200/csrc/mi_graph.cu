@@ -278,20 +278,22 @@ __global__ void composition_key_kernel(const int* __restrict__ Z, const int* __r
 
 // single CTA (1024 threads): stable sort by reward desc, first-occurrence dedupe by key, head, cutoff
 __global__ void __launch_bounds__(1024) replay_select_kernel(const unsigned long long* __restrict__ keys,
-                                                             const float* __restrict__ rewards, int n, int npow2,
-                                                             int buffer_size, float cutoff, int* __restrict__ out_idx,
+                                                             const double* __restrict__ rewards, int n, int npow2,
+                                                             int buffer_size, double cutoff, int* __restrict__ out_idx,
                                                              int* __restrict__ out_count) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    float* r = reinterpret_cast<float*>(sm_raw);            // [npow2]
+    // rewards are compared in float64 like the reference's pandas column (near-equal rewards and the strict cutoff test
+    // must not depend on an fp32 rounding)
+    double* r = reinterpret_cast<double*>(sm_raw);          // [npow2]
     int* id = reinterpret_cast<int*>(r + npow2);            // [npow2]
     const int tid = threadIdx.x;
     for (int i = tid; i < npow2; i += 1024) {
-        r[i] = (i < n) ? rewards[i] : -INFINITY;
+        r[i] = (i < n) ? rewards[i] : -(double)INFINITY;
         id[i] = (i < n) ? i : 0x7fffffff;
     }
     __syncthreads();
     // "a before b" : reward desc, NaN last, original index asc (stable)
-    auto before = [&](float ra, int ia, float rb, int ib) {
+    auto before = [&](double ra, int ia, double rb, int ib) {
         bool pa = ia == 0x7fffffff, pb = ib == 0x7fffffff;   // padding always last
         if (pa != pb) return pb;
         bool na = ra != ra, nb = rb != rb;
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(1024) replay_select_kernel(const unsigned long
                     bool up = (i & k) == 0;
                     bool sw = up ? before(r[p], id[p], r[i], id[i]) : before(r[i], id[i], r[p], id[p]);
                     if (sw) {
-                        float tr = r[i]; r[i] = r[p]; r[p] = tr;
+                        double tr = r[i]; r[i] = r[p]; r[p] = tr;
                         int ti = id[i]; id[i] = id[p]; id[p] = ti;
                     }
                 }
@@ -317,12 +319,12 @@ __global__ void __launch_bounds__(1024) replay_select_kernel(const unsigned long
     // dedupe: position p survives if no earlier position holds the same key (drop_duplicates keep='first')
     // reuse r[] as the keep flag afterwards, so read rewards back from global.
     for (int p = tid; p < npow2; p += 1024) {
-        float keep = 0.f;
+        double keep = 0.0;
         if (p < n) {
             unsigned long long kp = keys[id[p]];
-            keep = 1.f;
+            keep = 1.0;
             for (int q = 0; q < p; ++q)
-                if (keys[id[q]] == kp) { keep = 0.f; break; }
+                if (keys[id[q]] == kp) { keep = 0.0; break; }
         }
         r[p] = keep;   // each thread only touches its own slots of r[] here
     }
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(1024) replay_select_kernel(const unsigned long
         // head(buffer_size) of the survivors, then reward > cutoff (replay_buffer.py:60-71); n is small
         int rank = 0, m = 0;
         for (int p = 0; p < n; ++p) {
-            if (r[p] == 0.f) continue;
+            if (r[p] == 0.0) continue;
             if (rank < buffer_size && rewards[id[p]] > cutoff) out_idx[m++] = id[p];
             ++rank;
         }
@@ -392,8 +394,8 @@ extern "C" int mi_build_dst_csr(const int* seg_ptr, const int* edge_dst, int N, 
     return MI_OK;
 }
 
-extern "C" int mi_replay_select(const unsigned long long* keys, const float* rewards, int n, int buffer_size,
-                                float cutoff, int* out_idx, int* out_count, mi_stream_t stream) {
+extern "C" int mi_replay_select(const unsigned long long* keys, const double* rewards, int n, int buffer_size,
+                                double cutoff, int* out_idx, int* out_count, mi_stream_t stream) {
     MI_CHECK_ARG(out_count != nullptr, "null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     if (n <= 0) {
@@ -403,7 +405,7 @@ extern "C" int mi_replay_select(const unsigned long long* keys, const float* rew
     MI_CHECK_ARG(keys && rewards && out_idx && n <= 16384, "null pointer or n > 16384");
     int npow2 = 2;
     while (npow2 < n) npow2 <<= 1;
-    size_t smem = (size_t)npow2 * 8;
+    size_t smem = (size_t)npow2 * 12;
     if (smem > 48 * 1024)
         MI_CUDA(cudaFuncSetAttribute(replay_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     replay_select_kernel<<<1, 1024, smem, s>>>(keys, rewards, n, npow2, buffer_size, cutoff, out_idx, out_count);

@@ -4,14 +4,14 @@ Rows live in padded struct-of-arrays tensors in HBM (frac [cap, M, 3], Z [cap, M
 n [cap], reward [cap], key [cap]); the dedupe key is a 64-bit hash of the gcd-reduced element-count vector,
 i.e. the equivalence class of pymatgen's `composition.reduced_formula` (replay_buffer.py:38) computed by
 `mi_composition_key`; `extend` = concat -> sort by reward desc (stable) -> first occurrence per key ->
-head(buffer_size) -> reward > cutoff, done by the single-CTA `mi_replay_select` kernel; `sample` draws
+head(buffer_size) -> reward > cutoff, done by the single-CTA `mi_replay_select` kernel on float64 rewards; `sample` draws
 min(len, sample_size) rows uniformly without replacement with numpy's global RNG (what DataFrame.sample
 uses); `memory_purge` drops rows whose key matches a penalised structure."""
 import numpy as np
 import torch
 
 from .. import ops
-from ..models.diffcsp.sample import CrystalData
+from ..models.diffcsp.sample import CrystalBatch, CrystalData
 
 
 def _atomic_numbers(s):
@@ -21,6 +21,8 @@ def _atomic_numbers(s):
 
 
 class ReplayBuffer:
+    MAX_SELECT = 16384          # rows mi_replay_select sorts in one CTA
+
     def __init__(self, buffer_size=100, sample_size=8, reward_cutoff=0.0, device=None, max_atoms=None):
         self.buffer_size, self.sample_size, self.reward_cutoff = int(buffer_size), int(sample_size), float(reward_cutoff)
         self.device = torch.device(device if device is not None else "cuda")
@@ -30,21 +32,23 @@ class ReplayBuffer:
 
     # ------------------------------------------------------------------ packing
     def _pack(self, data, rewards):
+        """padded SoA rows of a list of crystals: concatenated on the host, ONE H2D copy per field, scattered into the
+        padded layout on the device (no per-crystal device copies: 10 k crystals per iteration in BASELINE configs[4])"""
         n = len(data)
-        M = max([self.M] + [int(d.num_atoms) for d in data])
         dev = self.device
+        cb = CrystalBatch(data)
+        na = cb.num_atoms.to(torch.int64)
+        M = max(self.M, int(na.max()))
+        row = torch.repeat_interleave(torch.arange(n), na).to(dev)
+        col = (torch.arange(int(na.sum())) - torch.repeat_interleave(torch.cumsum(na, 0) - na, na)).to(dev)
         frac = torch.zeros(n, M, 3, device=dev)
         Z = torch.zeros(n, M, dtype=torch.int32, device=dev)
-        lengths, angles = torch.zeros(n, 3, device=dev), torch.zeros(n, 3, device=dev)
-        na = torch.zeros(n, dtype=torch.int32, device=dev)
-        for i, d in enumerate(data):
-            k = int(d.num_atoms)
-            frac[i, :k] = torch.as_tensor(d.frac_coords).to(dev, torch.float32)
-            Z[i, :k] = torch.as_tensor(d.atom_types).to(dev, torch.int32)
-            lengths[i], angles[i] = d.lengths.reshape(3).to(dev), d.angles.reshape(3).to(dev)
-            na[i] = k
-        rew = torch.as_tensor(np.asarray(rewards, dtype=np.float64)).to(dev, torch.float32).reshape(n)
-        return dict(frac=frac, Z=Z, lengths=lengths, angles=angles, n=na, reward=rew)
+        frac[row, col] = cb.frac_coords.to(dev, torch.float32)
+        Z[row, col] = cb.atom_types.to(dev, torch.int32)
+        lengths = cb.lengths.to(dev, torch.float32).reshape(n, 3).contiguous()
+        angles = cb.angles.to(dev, torch.float32).reshape(n, 3).contiguous()
+        rew = torch.as_tensor(np.asarray(rewards, dtype=np.float64)).to(dev).reshape(n)     # float64, like the pandas column
+        return dict(frac=frac, Z=Z, lengths=lengths, angles=angles, n=na.to(dev, torch.int32), reward=rew)
 
     def keys_of(self, atomic_number_lists):
         """64-bit composition keys of a list of per-crystal atomic-number vectors."""
@@ -86,6 +90,21 @@ class ReplayBuffer:
         old = None if self._rows is None else {k: v[:self.count] for k, v in self._rows.items()}
         allr = self._cat(old, new)
         n = allr["reward"].shape[0]
+        if n > self.MAX_SELECT:
+            # beyond the single-CTA kernel's 16 384 rows: the same selection with device sorts (reward desc, stable;
+            # first occurrence per key; head; strict cutoff)
+            r, key = allr["reward"], allr["key"]
+            order = torch.argsort(r, descending=True, stable=True)
+            ks, perm = torch.sort(key[order], stable=True)
+            first = torch.ones(n, dtype=torch.bool, device=self.device)
+            first[1:] = ks[1:] != ks[:-1]
+            keep_pos = torch.sort(perm[first]).values[:self.buffer_size]
+            sel = order[keep_pos]
+            sel = sel[r[sel] > self.reward_cutoff]
+            self._rows = {k: v.index_select(0, sel).contiguous() for k, v in allr.items()}
+            self.count = int(sel.numel())
+            self.M = self._rows["frac"].shape[1]
+            return
         idx = torch.empty(n, dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         ops.replay_select(allr["key"], allr["reward"].contiguous(), n, self.buffer_size, self.reward_cutoff, idx, cnt)
@@ -106,7 +125,7 @@ class ReplayBuffer:
             n = int(r["n"][i])
             data.append(CrystalData(r["frac"][i, :n].cpu(), r["Z"][i, :n].cpu().to(torch.int64), r["lengths"][i].view(1, 3).cpu(),
                                     r["angles"][i].view(1, 3).cpu(), torch.tensor(n)))
-        return data, r["reward"][torch.as_tensor(pick, device=self.device)].double().cpu().numpy()
+        return data, r["reward"][torch.as_tensor(pick, device=self.device)].cpu().numpy()       # the stored float64 values
 
     def memory_purge(self, strucs):
         if self.count == 0 or len(strucs) == 0:

@@ -59,19 +59,29 @@ class CrystalLoader:
 
 
 def partition_crystals(num_atoms, world):
-    """Contiguous slices [start, end) per rank, balanced by sum n^2 (edge count)."""
+    """Contiguous slices [start, end) per rank, balanced by sum n^2 (edge count).  Every rank gets at least one crystal
+    when there are at least `world` of them (a 20-atom crystal next to 1-atom ones may cross several of the
+    total * r / world thresholds at once); with fewer crystals than ranks the trailing ranks get empty slices — they
+    contribute a zero gradient and still join every collective (FineTuner.run_batch)."""
     w = [int(n) * int(n) for n in num_atoms]
-    total, B = sum(w), len(w)
-    bounds, acc, r = [0], 0, 1
-    for i, v in enumerate(w):
-        acc += v
-        while r < world and acc >= total * r / world and len(bounds) < world:
-            bounds.append(i + 1)
-            r += 1
-    while len(bounds) < world:
-        bounds.append(B)
+    B, total = len(w), sum(w)
+    if B < world:                              # one crystal each for the first B ranks
+        return [(min(r, B), min(r + 1, B)) for r in range(world)]
+    prefix = [0]
+    for v in w:
+        prefix.append(prefix[-1] + v)
+    bounds = [0]
+    b = 0
+    for r in range(1, world):
+        target = total * r / world
+        while b < B and prefix[b] < target:
+            b += 1
+        if b > 0 and target - prefix[b - 1] < prefix[b] - target:        # the nearer of the two cuts
+            b -= 1
+        b = min(max(b, bounds[-1] + 1), B - (world - r))                  # strictly increasing, one left for each later rank
+        bounds.append(b)
     bounds.append(B)
-    return [(bounds[k], max(bounds[k], bounds[k + 1])) for k in range(world)]
+    return [(bounds[k], bounds[k + 1]) for k in range(world)]
 
 
 class FineTuner:
@@ -116,10 +126,9 @@ class FineTuner:
         Bg, Ng = len(na), sum(na)
         lo, hi = partition_crystals(na, self.world)[self.rank]
         n_lo, n_hi = sum(na[:lo]), sum(na[:hi])
-        if hi <= lo:
-            raise ValueError("rank %d got no crystals: need at least one crystal per rank" % self.rank)
-        local = _LocalBatch(agent, batch, lo, hi, n_lo, n_hi)
-        B, N = local.graph.B, local.graph.N
+        empty = hi <= lo        # fewer crystals than ranks: this rank adds a zero gradient and joins every collective
+        local = None if empty else _LocalBatch(agent, batch, lo, hi, n_lo, n_hi)
+        B, N = (0, 0) if empty else (local.graph.B, local.graph.N)
         reward = batch.reward.to(dev, torch.float32)[lo:hi].contiguous()
         w_kl = (self.sigma * (1.1 - reward)).contiguous()
         scale = 1.0 / (Bg * self.accum)
@@ -128,15 +137,28 @@ class FineTuner:
         ttab, ntab = agent.time_table(), agent.noise_table()
         costs = agent._costs()
         stats = torch.zeros(2, device=dev)
-        G = self.group_size(local.graph.E) if self.use_graph or self.group else 1
+        # every rank must cut the epoch into the same groups (noise is drawn per group for the GLOBAL batch): size them
+        # from the largest shard
+        parts = partition_crystals(na, self.world)
+        e_max = max(sum(n * n for n in na[a:b]) for a, b in parts)
+        G = self.group_size(e_max) if self.use_graph or self.group else 1
         groups = {}
+        used_graphs = []
 
         def make_group(Gn):
             """buffers + body for Gn stacked timesteps (slot j holds timestep t0 + j)"""
-            g = dec.graph_for(na[lo:hi] * Gn)
-            # global noise per slot (every rank draws the whole batch, uses its slice)
             z_l, z_x, z_a = (torch.empty(Gn, Bg, 3, 3, device=dev), torch.empty(Gn, Ng, 3, device=dev),
                              torch.empty(Gn, Ng, A, device=dev))
+            if empty:
+                def draw_only():
+                    if in_graph_noise:
+                        for j in range(Gn):
+                            noise.fill(z_l[j]), noise.fill(z_x[j]), noise.fill(z_a[j])
+                return dict(body=draw_only, z=(z_l, z_x, z_a), t_vec=torch.zeros(Gn, dtype=torch.int32, device=dev),
+                            graph=None, runs=0, eager=True)
+            g = dec.graph_for(na[lo:hi] * Gn)
+            used_graphs.append(g)
+            # global noise per slot (every rank draws the whole batch, uses its slice)
             if self.world > 1:      # this rank's crystals of every slot, contiguous (loss targets)
                 zl, zx, za = (torch.empty(Gn, B, 3, 3, device=dev), torch.empty(Gn, N, 3, device=dev),
                               torch.empty(Gn, N, A, device=dev))
@@ -168,7 +190,7 @@ class FineTuner:
                             scale, loss, kl, d, stats)
                 dec.backward_graph(g, temb, a_t, x_t, l_t, d[0], d[1], d[2], ws=ws_a)
 
-            return dict(body=body, z=(z_l, z_x, z_a), t_vec=t_vec, graph=None, runs=0)
+            return dict(body=body, z=(z_l, z_x, z_a), t_vec=t_vec, graph=None, runs=0, eager=False)
 
         t = 0
         while t < timesteps:
@@ -184,7 +206,7 @@ class FineTuner:
                     z_l[j].copy_(noise.step_randn((Bg, 3, 3)))
                     z_x[j].copy_(noise.step_randn((Ng, 3)))
                     z_a[j].copy_(noise.step_randn((Ng, A)))
-            if not self.use_graph or grp["runs"] == 0:
+            if not self.use_graph or grp["runs"] == 0 or grp["eager"]:
                 grp["body"]()
             else:
                 if grp["graph"] is None:
@@ -199,6 +221,11 @@ class FineTuner:
                 self.optimizer_step()
         if timesteps % self.accum != 0:
             self.optimizer_step()
+        # the stacked graphs and their workspaces (~70 KB per edge for the agent) belong to this batch order only: the
+        # loader reshuffles every epoch, so they are released here instead of piling up in the decoders' caches
+        groups.clear()
+        for g_ in used_graphs:
+            dec.release(g_), pdec.release(g_)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(stats, group=self.pg)

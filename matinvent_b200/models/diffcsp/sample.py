@@ -73,10 +73,14 @@ class CrystalBatch:
 class SampleDataset:
     """Atom counts drawn from the dataset prior with numpy's global RNG (sample.py:117-138)."""
 
-    def __init__(self, total_num, dataset="mp_20"):
+    def __init__(self, total_num, dataset="mp_20", num_atoms=None):
         self.total_num = total_num
         self.distribution = ATOM_DIST[dataset]
-        self.num_atoms = np.random.choice(len(self.distribution), total_num, p=self.distribution)
+        if num_atoms is not None:          # a shard of a draw made elsewhere (multi-GPU sampling)
+            assert len(num_atoms) == total_num
+            self.num_atoms = np.asarray(num_atoms, dtype=np.int64)
+        else:
+            self.num_atoms = np.random.choice(len(self.distribution), total_num, p=self.distribution)
 
     def __len__(self):
         return self.total_num
@@ -126,12 +130,16 @@ class DiffCSPSampler:
     target_compositions_dict: list | None = None
     num_atoms_distribution: str = "mp_20"
 
-    def generate(self, model: DiffCSPModule, batch_size=None, num_batches=None, noise=None, **kwargs) -> Tuple[List, List]:
+    def generate(self, model: DiffCSPModule, batch_size=None, num_batches=None, noise=None, num_atoms=None,
+                 **kwargs) -> Tuple[List, List]:
+        """`num_atoms` (optional): the atom counts to sample instead of drawing them (a rank's shard of the global draw);
+        further keyword arguments (`filter`, `max_num`, `mlip_opt` ... of the pipeline's sample_cfg) are ignored like
+        the reference's `**kwargs`."""
         batch_size = batch_size or self.batch_size
         num_batches = num_batches or self.num_batches
         assert batch_size is not None and num_batches is not None
         model.eval()
-        dataset = SampleDataset(batch_size * num_batches, self.num_atoms_distribution)
+        dataset = SampleDataset(batch_size * num_batches, self.num_atoms_distribution, num_atoms=num_atoms)
         step_lr = DEFAULT_STEP_LR["gen"][self.num_atoms_distribution]
         data_list = []
         for batch in dataset.batches(batch_size):

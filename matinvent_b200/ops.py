@@ -369,3 +369,22 @@ def replay_select(keys, rewards, n, buffer_size, cutoff, out_idx, out_count):
 
 def composition_key(Z, node_off, B, keys):
     check(lib().mi_composition_key(_p(Z), _p(node_off), B, _p(keys), _stream()), "mi_composition_key")
+
+
+def validity_prefilter(frac, L, lengths, node_off, B, mask, dmin=None, max_len=25.0, min_dist=0.5, min_vol=0.1, hard_len=40.0):
+    _f32(frac), _f32(L), _f32(lengths), _f32(dmin), _i32(node_off), _i32(mask)
+    check(lib().mi_validity_prefilter(_p(frac), _p(L), _p(lengths), _p(node_off), B, max_len, min_dist, min_vol, hard_len,
+                                      _p(mask), _p(dmin), _stream()), "mi_validity_prefilter")
+    return mask
+
+
+def composition_reward(Z, node_off, B, tables, mass, modes, targets, minv, maxv, tval, weight, reduce, props, rewards, failed):
+    _i32(Z), _i32(node_off), _i32(failed)
+    for t in (tables, mass, props, rewards):
+        if t.dtype != torch.float64 or not t.is_cuda:
+            raise TypeError("tables / mass / props / rewards must be CUDA float64 tensors")
+    P = len(modes)
+    ia, da = (C.c_int * P), (C.c_double * P)
+    check(lib().mi_composition_reward(_p(Z), _p(node_off), B, _p(tables), _p(mass), P, ia(*modes), ia(*targets), da(*minv),
+                                      da(*maxv), da(*tval), da(*weight), reduce, _p(props), _p(rewards), _p(failed), _stream()),
+          "mi_composition_reward")

@@ -1,7 +1,7 @@
 """RL pipeline base — mirror of pipeline/base.py:26-142 (`ReinL`): same constructor arguments, same config
 merge (suite config overridden by pipeline config, :53-59), same `reward_step`.  The long-term memory is the
-device-resident `memory.ltm.LongTimeMem` (pipeline/base.py:64 creates one unconditionally; here `ltm=True` does, and
-any object with the same methods is accepted); loggers and reward calculators of the reference are host-side
+device-resident `memory.ltm.LongTimeMem` (created unconditionally like pipeline/base.py:64; `ltm=<object>` substitutes any
+object with the same methods, `ltm=None` disables it); loggers and reward calculators of the reference are host-side
 bookkeeping / external property oracles (out of scope): duck-typed — pass the reference's
 objects or any stand-in."""
 import logging
@@ -17,7 +17,7 @@ from ..models.suite.base import get_device
 
 class ReinL:
     def __init__(self, rl_epoch, model_suite, reward, sample_cfg, finetune_cfg, save_dir, save_freq, device=None,
-                 logger=None, replay=False, replay_args=None, ltm=None, **kwargs):
+                 logger=None, replay=False, replay_args=None, ltm=True, **kwargs):
         self.rl_epoch = rl_epoch
         self.model_suite = model_suite
         self.reward = reward

@@ -575,7 +575,10 @@ def reduced_composition_key(atom_types):
 
 class ReplayBufferOracle:
     """memory/replay_buffer.py:11-104 restated on plain lists (no pandas).  Ties in reward keep the
-    earlier row (a stable sort; pandas' quicksort leaves tie order unspecified)."""
+    earlier row (a stable sort; pandas' quicksort leaves tie order unspecified).  PINNED: row-for-row equal to the
+    unmodified reference class after every extend / sample / memory_purge of a random call sequence
+    (tests/test_oracle_vs_reference.py::test_replay_buffer_oracle_matches_live_reference); `sample(np.random)`
+    consumes numpy's global RNG exactly like `DataFrame.sample` does."""
 
     def __init__(self, buffer_size=100, sample_size=8, reward_cutoff=0.0):
         self.buffer_size, self.sample_size, self.reward_cutoff = buffer_size, sample_size, reward_cutoff

@@ -140,6 +140,7 @@ def baseline_forward():
     gold["ft"] = {k: ft[k] for k in keep}
     gold["ft_grad_checks"] = {k: dict(abs_sum=float(v.double().abs().sum()), head=v.reshape(-1)[:64].clone())
                               for k, v in grads.items()}
+    gold["ft_grad_proj"] = grad_projections(grads)
     gold["checksums_prior"] = checksums(sdp)
     gold["ft_seconds"] = time.time() - t1
     torch.save(gold, os.path.join(GOLD, "baseline_forward.pt"))
@@ -147,15 +148,96 @@ def baseline_forward():
           (int(c["num_atoms"].sum()), gold["edges"], gold["seconds"]))
 
 
+def _bench_atom_counts(n):
+    """bench.py's draw: np.random.RandomState(0).choice over the reference's ATOM_DIST['mp_20'] literal (read from the
+    source: importing models/diffcsp/sample.py pulls in pymatgen)"""
+    import ast
+    import numpy as np
+    src = open(os.path.join(R.REF_ROOT, "models", "diffcsp", "sample.py")).read()
+    node = next(n_ for n_ in ast.parse(src).body if isinstance(n_, ast.Assign) and
+                getattr(n_.targets[0], "id", "") == "ATOM_DIST")
+    dist = ast.literal_eval(node.value)["mp_20"]
+    return np.random.RandomState(0).choice(len(dist), n, p=dist).tolist()
+
+
+def grad_projections(grads, n_proj=4):
+    """position- and sign-sensitive fingerprints of a gradient set: for every tensor, its L2 norm and the inner products
+    with `n_proj` seeded standard-normal tensors (seed = crc32 of the parameter name + projection index).  A transposed,
+    permuted or sign-flipped block moves a projection by ~ the block's norm; |.|-sums and a 64-element head do not see it."""
+    import zlib
+    out = {}
+    for k, v in grads.items():
+        v64 = v.detach().double().reshape(-1)
+        proj = []
+        for j in range(n_proj):
+            g = torch.Generator().manual_seed(zlib.crc32(("%s#%d" % (k, j)).encode()))
+            r = torch.randn(v64.numel(), generator=g, dtype=torch.float64)
+            proj.append(float(torch.dot(v64, r)))
+        out[k] = dict(norm=float(v64.norm()), proj=proj)
+    return out
+
+
+def add_grad_projections():
+    """re-run the two full-size fine-tune timesteps of the UNMODIFIED reference (4 crystals: full_net.pt, 256 crystals:
+    baseline_forward.pt) and add `ft_grad_proj` to the existing fixtures (everything else in them is left as it is)"""
+    hp = O.default_hparams()
+    sn = torch.load(os.path.join(GOLD, "sigmas_norm_T1000.pt"))["sigmas_norm"]
+    ref, prior, sd, sdp = build(hp, sigmas_norm=sn)
+    for fname, num_atoms in (("full_net.pt", [4, 11, 20, 8]), ("baseline_forward.pt", [max(1, n) for n in _bench_atom_counts(256)])):
+        gold = torch.load(os.path.join(GOLD, fname), weights_only=False)
+        ft, grads = ft_case(hp, ref, prior, num_atoms, 300)
+        assert torch.equal(ft["num_atoms"], gold["ft"]["num_atoms"])
+        worst = 0.0
+        for k, chk in gold["ft_grad_checks"].items():      # the re-run reproduces the stored fingerprints
+            worst = max(worst, abs(float(grads[k].double().abs().sum()) - chk["abs_sum"]) / (chk["abs_sum"] + 1e-300))
+        assert worst < 1e-6, worst
+        gold["ft_grad_proj"] = grad_projections(grads)
+        torch.save(gold, os.path.join(GOLD, fname))
+        print("%s: ft_grad_proj added (%d tensors; re-run vs stored abs-sums: %.1e)" % (fname, len(grads), worst))
+
+
+def baseline_trajectory(T=100, seed=7):
+    """A complete T-step `DiffCSPModule.sample` of the UNMODIFIED reference (full-size net) on the benchmark's batch of
+    256 mp_20 crystals (34 445 edges) under a noise tape: the multi-step behaviour of the configuration bench.py
+    measures, where the CUDA path runs its per-edge GEMMs on the merged 128x256 single-accumulator tiles.  The
+    schedules are the reference's own for `timesteps=T` (the whole sigma / beta range in T steps); its Monte-Carlo
+    sigmas_norm buffer is stored.  Kept: the final state (atom types as argmax int8 + every 8th row of the
+    continuous state), coordinates and lattices at four intermediate steps."""
+    hp = O.default_hparams(timesteps=T)
+    ref, prior, sd, sdp = build(hp)
+    num_atoms = _bench_atom_counts(256)
+    batch = R.make_batch(num_atoms)
+    t0 = time.time()
+    with noise_tape(seed):
+        out, traj = ref.sample(batch, step_lr=5e-6)
+    keep = sorted(set([T - 1, (3 * T) // 4, T // 2, T // 4, 1]))
+    gold = dict(hp=hp, seed_weights=0, checksums=checksums(sd), num_atoms=torch.tensor(num_atoms), seed=seed, step_lr=5e-6,
+                sigmas_norm=ref.sigma_scheduler.sigmas_norm.clone(), seconds=time.time() - t0,
+                ref_frac_coords=out["frac_coords"].clone(), ref_lattices=out["lattices"].clone(),
+                ref_types_argmax=out["atom_types"].argmax(-1).to(torch.int8),
+                ref_atom_types_rows8=out["atom_types"][::8].clone(),
+                ref_traj={t: {k: traj[t][k].clone() for k in ("frac_coords", "lattices")} for t in keep})
+    torch.save(gold, os.path.join(GOLD, "baseline_traj.pt"))
+    print("baseline_traj.pt written: %d crystals, %d steps, reference sample %.1f s" % (len(num_atoms), T, gold["seconds"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the full-size net incl. a 1000-step sample (minutes)")
     ap.add_argument("--baseline", action="store_true",
                     help="only: one forward of the full-size net on the benchmark batch (256 mp_20 crystals)")
+    ap.add_argument("--baseline-traj", action="store_true",
+                    help="only: a complete 100-step sample of the full-size net on the benchmark batch (minutes)")
+    ap.add_argument("--grad-projections", action="store_true",
+                    help="only: add seeded random projections of the full-size reference gradients to the fixtures")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     if args.baseline:
         return baseline_forward()
+    if args.baseline_traj:
+        return baseline_trajectory()
+    if args.grad_projections:
+        return add_grad_projections()
 
     # --- Monte-Carlo sigmas_norm buffer for T=1000 (copied, never recomputed: SURVEY.md §7 hard parts)
     hp_full = O.default_hparams()
@@ -205,6 +287,7 @@ def main():
         gold["ft"] = ft
         gold["ft_grad_checks"] = {k: dict(abs_sum=float(v.double().abs().sum()), head=v.reshape(-1)[:64].clone())
                                   for k, v in grads.items()}
+        gold["ft_grad_proj"] = grad_projections(grads)
         gold["sample_T1000"] = sample_case(hp, ref, num_atoms, 7)
         print("1000-step reference sample took %.1f s" % gold["sample_T1000"]["seconds"])
         torch.save(gold, os.path.join(GOLD, "full_net.pt"))

@@ -83,6 +83,26 @@ def make_batch(num_atoms, **extra):
     return b
 
 
+def _import_memory_module(fname, modname):
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    for p in (REF_ROOT, _SHIMS):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, _SHIMS)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF_ROOT, "memory", fname))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def import_reference_replay_buffer():
+    """The reference's `memory.replay_buffer.ReplayBuffer`, unmodified (same two type-hint imports as ltm.py)."""
+    return _import_memory_module("replay_buffer.py", "_ref_memory_replay_buffer").ReplayBuffer
+
+
 def import_reference_ltm():
     """The reference's `memory.ltm.LongTimeMem`, unmodified (pandas is installed; its pymatgen / PyG imports are type
     hints, stubbed under oracle/shims)."""
@@ -98,3 +118,19 @@ def import_reference_ltm():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.LongTimeMem
+
+
+def import_reference_reward():
+    """The reference's `rewards.reward` module, unmodified (numpy only; omegaconf / pymatgen names stubbed under shims)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    for p in (REF_ROOT, _SHIMS):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, _SHIMS)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_rewards_reward", os.path.join(REF_ROOT, "rewards", "reward.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

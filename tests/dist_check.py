@@ -60,11 +60,12 @@ def main():
             return DiffCSPSampler(batch_size=6, num_batches=1)
         def load_model(self):
             return build_module(hp, gs["sd"], gs["sigmas_norm"], device=dev)
-    np.random.seed(100 + rank)
-    torch.manual_seed(100 + rank)
+    np.random.seed(100)             # every rank runs the loop with the SAME seeds (pipeline/mat_invent.py docstring): the
+    torch.manual_seed(100)          # global atom-count draw, the fine-tune shuffle and the replay picks are rank-identical
     import tempfile
-    pipe = MatInvent(rl_epoch=1, model_suite=_Suite(), reward=None, sample_cfg={}, finetune_cfg={}, save_dir=tempfile.mkdtemp(),
-                     save_freq=1, device=str(dev))
+    pipe = MatInvent(rl_epoch=1, model_suite=_Suite(), reward=None, sample_cfg=dict(invalid_filter=False), finetune_cfg={},
+                     save_dir=tempfile.mkdtemp(),
+                     save_freq=1, device=str(dev), save_samples=False)
     data, strucs, _, _ = pipe.sample_step()
     assert len(data) == 6 and len(strucs) == 6, len(data)
     sizes = torch.tensor([int(d.num_atoms) for d in data], device=dev)
@@ -72,6 +73,13 @@ def main():
     dist.all_gather(all_sizes, sizes)
     for t in all_sizes[1:]:
         assert torch.equal(all_sizes[0], t), "ranks disagree on the gathered sample list"
+    # the union over ranks is the draw a single process makes from the same numpy stream, and ranks sampled with
+    # different noise streams (identical crystals would mean a shared stream)
+    np.random.seed(100)
+    from matinvent_b200.models.diffcsp.sample import SampleDataset
+    assert [max(int(n), 1) for n in SampleDataset(6).num_atoms.tolist()] == sizes.tolist()
+    fr = [d.frac_coords for d in data]
+    assert not any(a.shape == b.shape and torch.equal(a, b) for i, a in enumerate(fr) for b in fr[i + 1:])
     if rank == 0:
         print("DIST_CHECK_OK", logs_multi)
     dist.destroy_process_group()

@@ -119,6 +119,24 @@ def test_ft_timestep_gradients_small(gold_small):
     assert worst[0] < 1e-4, worst
 
 
+def _check_grad_projections(grads, proj, tol=1e-4):
+    """seeded random projections <g, r> of every gradient tensor against the unmodified reference's (oracle/make_golden.py
+    grad_projections): |<g - g_ref, r>| <= tol * ||g_ref||_2, i.e. a relative-L2 bar that sees sign flips, transposes and
+    permuted blocks anywhere in the tensor"""
+    import zlib
+    worst = (0.0, None)
+    for k, chk in proj.items():
+        v = grads[k].detach().double().cpu().reshape(-1)
+        for j, ref in enumerate(chk["proj"]):
+            g = torch.Generator().manual_seed(zlib.crc32(("%s#%d" % (k, j)).encode()))
+            r = torch.randn(v.numel(), generator=g, dtype=torch.float64)
+            err = abs(float(torch.dot(v, r)) - ref) / (chk["norm"] + 1e-300)
+            worst = max(worst, (err, k))
+            assert err < tol, (k, j, err)
+        assert abs(float(v.norm()) - chk["norm"]) < tol * chk["norm"] + 1e-30, k
+    return worst
+
+
 def _full_module(gold_full, which=0):
     from oracle import diffcsp_oracle as O
     hp = gold_full["hp"]
@@ -160,6 +178,8 @@ def test_ft_gradients_full_size(gold_full):
         assert abs(float(g.double().abs().sum()) - chk["abs_sum"]) < 1e-4 * chk["abs_sum"] + 1e-12, k
         scale = float(g.abs().max()) + 1e-30
         assert float((g.reshape(-1)[:64] - chk["head"]).abs().max()) < 1e-4 * scale, k
+    worst = _check_grad_projections(grads, gold_full["ft_grad_proj"])
+    print("full-size fine-tune gradients vs reference: worst projection error %.2e of the tensor's norm (%s)" % worst)
 
 
 def test_sample_full_size_1000_steps(gold_full):
@@ -175,6 +195,23 @@ def test_sample_full_size_1000_steps(gold_full):
         assert rel_err(traj[t]["lattices"], ref["lattices"]) < 1e-4, t
     print("1000-step parity: frac %.2e  lattice %.2e" % (wrapped_err(out["frac_coords"], s["ref_frac_coords"]),
                                                          rel_err(out["lattices"], s["ref_lattices"])))
+    assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
+    assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
+    assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
+
+
+def test_sample_full_size_1000_steps_merged_tiles(gold_full, monkeypatch):
+    """the same 1000-step reference golden with the per-edge GEMMs FORCED onto the merged 128x256 single-accumulator
+    tiles (the format the benchmark batch uses; 4 crystals would not select it): 2 000 chained evaluations of it"""
+    from matinvent_b200.models.diffcsp import TapeNoise
+    from oracle.ref_import import make_batch
+    monkeypatch.setenv("MI_TC_FORCE_MERGED", "1")
+    s = gold_full["sample_T1000"]
+    m = _full_module(gold_full)
+    assert m.decoder.edge_mode(int((s["num_atoms"] ** 2).sum())) == (True, True)
+    out, _ = m.sample(make_batch(s["num_atoms"].tolist()), step_lr=s["step_lr"], noise=TapeNoise("cuda", seed=s["seed"]))
+    print("1000-step parity (merged tiles forced): frac %.2e  lattice %.2e" % (
+        wrapped_err(out["frac_coords"], s["ref_frac_coords"]), rel_err(out["lattices"], s["ref_lattices"])))
     assert wrapped_err(out["frac_coords"], s["ref_frac_coords"]) < 1e-4
     assert rel_err(out["lattices"], s["ref_lattices"]) < 1e-4
     assert torch.equal(_types(out["atom_types"]), _types(s["ref_atom_types"]))
@@ -196,23 +233,37 @@ def test_sample_full_size_1000_steps_ffma_path(gold_full):
 
 
 def test_generate_plugin_api(gold_small):
-    """DiffCSPSampler.generate (models/diffcsp/sample.py:148-201): shapes, ranges, post-processing vs oracle."""
+    """DiffCSPSampler.generate (models/diffcsp/sample.py:148-201) through the plugin call, two batches on one noise tape:
+    every returned crystal against the oracle's sampler + post-processing (argmax + 1, lattice -> lengths / angles,
+    per-crystal split) on the same atom-count draw and the same tape"""
     import numpy as np
     from oracle import diffcsp_oracle as O
-    from matinvent_b200.models.diffcsp import DiffCSPSampler
+    from matinvent_b200.models.diffcsp import DiffCSPSampler, TapeNoise
+    from matinvent_b200.models.diffcsp.sample import ATOM_DIST, DEFAULT_STEP_LR
     gs = gold_small
-    m = build_module(gs["hp"], gs["sd"], gs["sigmas_norm"])
+    hp, sd = gs["hp"], gs["sd"]
+    m = build_module(hp, sd, gs["sigmas_norm"])
     np.random.seed(0)
-    torch.manual_seed(0)
-    data, strucs = DiffCSPSampler(batch_size=6, num_batches=2).generate(m, filter=None, max_num=3)
+    data, strucs = DiffCSPSampler(batch_size=6, num_batches=2).generate(m, noise=TapeNoise("cuda", seed=21), filter=None,
+                                                                        max_num=3)
     assert len(data) == len(strucs) == 12
-    for d in data:
+    np.random.seed(0)
+    na = np.random.choice(len(ATOM_DIST["mp_20"]), 12, p=ATOM_DIST["mp_20"]).tolist()
+    noise = O.Noise(torch.Generator().manual_seed(21))
+    sch = O.Schedules(hp, gs["sigmas_norm"])
+    ref = []
+    for b in range(2):
+        out = O.sample(sd, hp, sch, na[6 * b:6 * b + 6], noise, step_lr=DEFAULT_STEP_LR["gen"]["mp_20"])
+        ref += O.generate_postprocess(out)
+    for d, r in zip(data, ref):
         n = int(d.num_atoms)
-        assert 1 <= n <= 20 and d.frac_coords.shape == (n, 3) and d.atom_types.shape == (n,)
+        assert n == r["num_atoms"] and d.frac_coords.shape == (n, 3) and d.atom_types.shape == (n,)
         assert d.lengths.shape == (1, 3) and d.angles.shape == (1, 3)
-        assert int(d.atom_types.min()) >= 1 and int(d.atom_types.max()) <= 100
-        assert float(d.frac_coords.min()) >= 0 and float(d.frac_coords.max()) <= 1
-        assert torch.isfinite(d.lengths).all() and torch.isfinite(d.angles).all()
+        assert torch.equal(d.atom_types.long(), r["atom_types"].long())
+        assert wrapped_err(d.frac_coords, r["frac_coords"]) < 1e-4
+        assert rel_err(d.lengths, r["lengths"]) < 1e-4
+        assert float((d.angles - r["angles"]).abs().max()) < 1e-2          # degrees
+        assert 1 <= int(d.atom_types.min()) and int(d.atom_types.max()) <= 100
 
 
 # ------------------------------------------------------------------------------------ knn edges
@@ -369,6 +420,38 @@ def test_ft_gradients_baseline_batch_vs_reference_golden(gold_full, gold_baselin
         worst = max(worst, float((g.reshape(-1)[:64] - chk["head"]).abs().max()) / scale)
         assert float((g.reshape(-1)[:64] - chk["head"]).abs().max()) < 1e-4 * scale, k
     print("baseline-batch fine-tune gradients vs reference golden: worst head error %.2e of the tensor's max" % worst)
+    worst = _check_grad_projections(grads, gold_baseline["ft_grad_proj"])
+    print("baseline-batch fine-tune gradients vs reference: worst projection error %.2e of the tensor's norm (%s)" % worst)
+
+
+def test_sample_baseline_batch_vs_reference_trajectory():
+    """The benchmark configuration's multi-step behaviour against the UNMODIFIED reference: a complete 100-step
+    DiffCSPModule.sample (the reference's own T=100 schedules) of the 256-crystal batch under a shared noise tape
+    (tests/golden/baseline_traj.pt, oracle/make_golden.py --baseline-traj).  200 chained score-network evaluations on
+    the merged 128x256 tiles (and the fused scatter epilogue), north-star tolerances."""
+    from conftest import load_gold
+    from oracle import diffcsp_oracle as O
+    from oracle.ref_import import make_batch
+    from matinvent_b200.models.diffcsp import TapeNoise
+    gt = load_gold("baseline_traj.pt")
+    hp = gt["hp"]
+    sd = O.init_params(hp, gt["seed_weights"])
+    for k, v in sd.items():
+        assert abs(float(v.double().abs().sum()) - gt["checksums"][k]) <= 1e-9 * max(1.0, gt["checksums"][k]), k
+    m = build_module(hp, sd, gt["sigmas_norm"])
+    na = gt["num_atoms"]
+    assert m.decoder.edge_mode(int((na * na).sum())) == (True, True)
+    out, traj = m.sample(make_batch(na.tolist()), step_lr=gt["step_lr"], noise=TapeNoise("cuda", seed=gt["seed"]),
+                         return_traj=True)
+    for t, ref in gt["ref_traj"].items():
+        ef, el = wrapped_err(traj[t]["frac_coords"], ref["frac_coords"]), rel_err(traj[t]["lattices"], ref["lattices"])
+        print("baseline-batch trajectory vs reference, step %3d: frac %.2e lattice %.2e" % (t, ef, el))
+        assert ef < 1e-4 and el < 1e-4, t
+    ef, el = wrapped_err(out["frac_coords"], gt["ref_frac_coords"]), rel_err(out["lattices"], gt["ref_lattices"])
+    print("baseline-batch 100-step sample vs reference: frac %.2e lattice %.2e" % (ef, el))
+    assert ef < 1e-4 and el < 1e-4
+    assert torch.equal(out["atom_types"].argmax(-1).cpu().to(torch.int8), gt["ref_types_argmax"])
+    assert rel_err(out["atom_types"][::8], gt["ref_atom_types_rows8"]) < 1e-4
 
 
 def test_gradients_baseline_batch_merged_vs_ffma(gold_full):

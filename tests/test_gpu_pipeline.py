@@ -180,7 +180,9 @@ def test_rl_loop_plumbing(tmp_path):
     np.random.seed(0)
     torch.manual_seed(0)
     suite = _suite(tmp_path)
-    pipe = MatInvent(rl_epoch=2, model_suite=suite, reward=StandInHHIReward(), sample_cfg=dict(filter=None, max_num=4),
+    # a random-init net puts atoms anywhere: only the in-tree cell-length rule filters here (structure_validity=False)
+    pipe = MatInvent(rl_epoch=2, model_suite=suite, reward=StandInHHIReward(),
+                     sample_cfg=dict(filter=None, max_num=4, structure_validity=False),
                      finetune_cfg=dict(batch_size=4, accum_steps=5, epochs=1, sigma=0.025), save_dir=str(tmp_path),
                      save_freq=1, device="cuda", replay=True, replay_args=dict(buffer_size=10, sample_size=2, reward_cutoff=0.0))
     w0 = pipe.agent.decoder.flat.data.clone()
@@ -188,8 +190,36 @@ def test_rl_loop_plumbing(tmp_path):
     pipe.run_rl()
     assert not torch.equal(pipe.agent.decoder.flat.data, w0) and torch.equal(pipe.prior.decoder.flat.data, p0)
     assert torch.isfinite(pipe.agent.decoder.flat.data).all()
-    assert len(pipe.replay) > 0 and pipe.cost == 16
+    # max_num caps what is scored (pipeline/mat_invent.py:110-114): 2 iterations x min(8 sampled, 4) crystals
+    assert len(pipe.replay) > 0 and pipe.cost == 8
     assert os.path.isfile(tmp_path / "models" / "final" / "last.ckpt")
+    # the reference's per-iteration dumps: valid / eval extxyz and the long-term-memory csv (:82-86, 117-121, 212)
+    from matinvent_b200.pipeline.utils import read_extxyz
+    assert len(read_extxyz(str(tmp_path / "samples" / "step_0001_valid.extxyz"))) == 8
+    assert len(read_extxyz(str(tmp_path / "samples" / "step_0001_eval.extxyz"))) == 4
+    assert os.path.isfile(tmp_path / "samples" / "long_term_memory.csv") and len(pipe.ltm) == 8
+    assert set(pipe.timing) >= {"sample_s", "filter_s", "reward_s", "memory_s", "finetune_s", "total_s"}
+
+
+def test_rl_step_device_reward_and_filter(tmp_path):
+    """one RL iteration with every post-sampling stage on the device: validity pre-filter, multi-objective composition
+    reward (min of two scaled properties, BASELINE configs[4] style), diversity filter, replay buffer"""
+    from matinvent_b200.pipeline import MatInvent
+    from matinvent_b200.rewards import CompositionReward, synthetic_table
+    np.random.seed(1)
+    torch.manual_seed(1)
+    suite = _suite(tmp_path, sample_cfg=dict(batch_size=32, num_batches=1))
+    reward = CompositionReward(
+        prop_cfg=[dict(name="hhi", table=synthetic_table("hhi"), target="descending", minv=750, maxv=3250),
+                  dict(name="magmom", table=synthetic_table("magmom"), weights="atom", target="ascending", minv=0.0, maxv=0.25)],
+        reward_threshold=0.8, reduce="min", device="cuda")
+    pipe = MatInvent(rl_epoch=1, model_suite=suite, reward=reward, sample_cfg=dict(structure_validity=False),
+                     finetune_cfg=dict(batch_size=8, accum_steps=5, epochs=1, sigma=0.025), save_dir=str(tmp_path), save_freq=1,
+                     device="cuda", replay=True, replay_args=dict(buffer_size=10, sample_size=2, reward_cutoff=0.0),
+                     div_filter=True, df_args=dict(tol=3, buff=6))
+    log, logs = pipe.rl_step()
+    assert pipe.cost <= 32 and "hhi mean" in log and "magmom std" in log and log["crystal_num"] == len(pipe.ltm)
+    assert len(logs) == 1 and np.isfinite(logs[0]["loss"])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

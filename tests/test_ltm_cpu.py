@@ -47,19 +47,3 @@ def test_empty_memory_and_empty_query():
     m.extend_keys(torch.as_tensor([1]), torch.as_tensor([1]), [0.5], 0)
     r, pen, a, b = m.div_filter_keys(torch.zeros(0, dtype=torch.int64), [])
     assert r.shape == (0,) and pen == []
-
-
-def test_cell_length_prefilter_matches_reference_rule():
-    """pipeline/filters/opt_filter.py:50-63: keep crystals whose longest cell edge is below 25 A (strictly)"""
-    import types
-    from matinvent_b200.pipeline.filters import cell_length_mask, invalid_filter
-    L = torch.tensor([[3.0, 4.0, 5.0], [25.0, 2.0, 2.0], [24.999, 24.0, 1.0], [1.0, 30.0, 2.0]])
-    data = [types.SimpleNamespace(lengths=l.view(1, 3)) for l in L]
-    strucs = ["s%d" % i for i in range(4)]
-    want = np.array([max(l.tolist()) < 25 for l in L])
-    assert (cell_length_mask(data) == want).all() and want.tolist() == [True, False, True, False]
-    kept_d, kept_s = invalid_filter(data, strucs)
-    assert kept_s == ["s0", "s2"] and len(kept_d) == 2
-    m = invalid_filter(data, strucs, return_mask=True, structure_validity=lambda s: s != "s0")
-    assert m.tolist() == [False, False, True, False]
-    assert cell_length_mask([]).shape == (0,)

@@ -80,3 +80,78 @@ def test_long_term_memory_oracle_matches_live_reference():
                 assert m1 == m2, (m1, m2)
             assert abs(ref.get_baseline(step) - ora.get_baseline(step)) < 1e-15
             assert len(ref) == len(ora.memory) and len(ref.unique_comps) == len(ora.unique_comps)
+
+
+def test_replay_buffer_oracle_matches_live_reference():
+    """oracle.diffcsp_oracle.ReplayBufferOracle against the UNMODIFIED memory/replay_buffer.py:11-104 (pandas) driven with
+    duck-typed structures: extend (dedupe by reduced formula keeping the best, top-K, strict cutoff), sample (numpy's
+    global RNG, without replacement), memory_purge — same rows in the same order after every call."""
+    import types
+    import warnings
+    import numpy as np
+    RefRB = R.import_reference_replay_buffer()
+
+    def struc(formula, elements):
+        return types.SimpleNamespace(composition=types.SimpleNamespace(reduced_formula=formula), species=list(elements))
+
+    names = [("TiO2", ("Ti", "O")), ("FeO", ("Fe", "O")), ("Fe2O3", ("Fe", "O")), ("LiPO4", ("Li", "P", "O")), ("TiO", ("Ti", "O")),
+             ("NaCl", ("Na", "Cl")), ("KBr", ("K", "Br")), ("MgO", ("Mg", "O")), ("Al2O3", ("Al", "O")), ("SiC", ("Si", "C"))]
+    rng = np.random.default_rng(5)
+    for size, ssize, cutoff in ((6, 3, 0.1), (100, 10, 0.1), (4, 8, 0.0)):
+        ref, ora = RefRB(size, ssize, cutoff), O.ReplayBufferOracle(size, ssize, cutoff)
+        uid = 0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for it in range(12):
+                pick = [names[i] for i in rng.integers(0, len(names), 7)]
+                rew = rng.random(7)
+                if it == 3:
+                    rew[:] = 0.05          # everything at or under the cutoff
+                data = list(range(uid, uid + 7))
+                uid += 7
+                ref.extend(data, [struc(f, e) for f, e in pick], rew)
+                ora.extend(data, [f for f, _ in pick], rew)
+                assert ref.buffer["data"].tolist() == [r[0] for r in ora.rows]
+                assert ref.buffer["comp"].tolist() == [r[1] for r in ora.rows]
+                assert np.array_equal(ref.buffer["reward"].values.astype(float), np.array([r[2] for r in ora.rows]))
+                np.random.seed(100 + it)
+                d1, r1 = ref.sample()
+                np.random.seed(100 + it)
+                d2, r2 = ora.sample(np.random)
+                assert list(d1) == list(d2) and np.array_equal(np.asarray(r1, dtype=float), np.asarray(r2, dtype=float))
+                if it % 4 == 2:
+                    bad = [names[i] for i in rng.integers(0, len(names), 2)]
+                    ref.memory_purge([struc(f, e) for f, e in bad])
+                    ora.memory_purge([f for f, _ in bad])
+                    assert ref.buffer["data"].tolist() == [r[0] for r in ora.rows]
+                assert len(ref) == len(ora)
+
+
+def test_reward_scoring_oracle_matches_live_reference(tmp_path):
+    """oracle.pipeline_oracle.reward_scoring against the UNMODIFIED rewards/reward.py:33-115 (`Reward.scoring`) driven with
+    stub calculators: every target kind, every reduce mode, NaN (failed) samples — bit for bit"""
+    import types
+    import numpy as np
+    from oracle import pipeline_oracle as P
+    mod = R.import_reference_reward()
+    rng = np.random.default_rng(3)
+    B = 40
+    raw = [rng.normal(2000, 1500, B), rng.random(B) * 0.4, rng.normal(3.0, 1.5, B)]
+    raw[0][[3, 17]] = np.nan
+    raw[2][[17, 30]] = np.nan
+    cfgs = [dict(name="hhi", target="descending", minv=750, maxv=3250, weight=0.5),
+            dict(name="magmom", target="ascending", minv=0.0, maxv=0.25, weight=0.3),
+            dict(name="band_gap", target=3.0, minv=0.0, maxv=2.0, weight=0.2)]
+
+    def calc_of(arr):
+        return types.SimpleNamespace(calc=lambda samples, label: arr.copy())
+
+    for reduce in ("mean", "min", "weight"):
+        for sel in ([0], [0, 1], [0, 1, 2], [2]):
+            prop_cfg = [types.SimpleNamespace(calculator=calc_of(raw[i]), **cfgs[i]) for i in sel]
+            ref = mod.Reward(root_dir=str(tmp_path), prop_cfg=prop_cfg, reward_threshold=0.8, reduce=reduce)
+            r1, d1, f1 = ref.scoring(([None] * B, None), "x")
+            r2, d2, f2 = P.reward_scoring([raw[i] for i in sel], [cfgs[i] for i in sel], reduce)
+            assert np.array_equal(r1, r2) and np.array_equal(f1, f2), (reduce, sel)
+            for k in d1:
+                assert np.array_equal(d1[k], d2[k]), k
