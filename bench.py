@@ -8,15 +8,24 @@ reverse diffusion (2 000 score-network evaluations) of `--batch` crystals per GP
 upstream default size (hidden 512, 6 layers, 128 frequencies, fully-connected edges), synthetic
 random-init weights and mp_20 atom counts.  One JSON line is printed by rank 0.
 
-value      device-resident throughput (CUDA events, max over ranks; Philox noise generated in-graph)
+value      device-resident throughput, WEAK scaling: `--batch` (256, the batch size of BASELINE configs[1]) crystals per
+           GPU, the N x 256 drawn crystals cut into contiguous shards balanced by sum n^2 (CUDA events, max over ranks;
+           Philox noise generated in-graph)
+strong_scaling   the same sampler on a FIXED global batch of 1024 crystals (BASELINE configs[2]) sharded over the N GPUs
+           (N = 1 runs all 1024): the north-star's strong-scaling axis
 e2e        same metric through the reference-facing plugin call DiffCSPSampler.generate(): initial noise
            drawn on the HOST and copied H2D, per-step noise from torch's device generator, results
            post-processed and copied D2H — all inside the timed region
+fine_tune_step   the reward-weighted fine-tune step (pipeline/mat_invent.py:125-189) at the reference's working point
+           (18 crystals, accum_steps 50) sharded over the N GPUs, gradient all-reduce + flat Adam inside the timed epoch;
+           at N > 1 also the all-reduce of the 49 MB gradient buffer on its own (us, bus GB/s)
 roofline   dominant kernel (the per-edge GEMMs) — achieved algorithmic TFLOP/s over the measured peak
-cpu_baseline  the reference's CPU path restated in oracle/ (the reference itself cannot travel to the
-           GPU box), timed on this box's host cores on a bounded sample
+cpu_baseline  the UNMODIFIED reference sampler (models/diffcsp/diffusion.py DiffCSPModule.sample, staged under
+           baseline/_ref/ by __graft_entry__.build(), imported under oracle/shims) on this box's host cores, bounded sample
+gpu_reference   Comparator B: the same unmodified reference code `.cuda()` on this B200 — the same
+           256-crystal batch, all 1000 steps — i.e. what a user of the reference gets on this box today
 
-`--impl reference` times only that CPU path and prints the same line shape.
+`--impl reference` times only the reference's CPU path and prints the same line shape.
 """
 import argparse
 import json
@@ -113,31 +122,86 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
 
 
-def cpu_reference_leg(na_all, state_dict, seconds_target=20.0, ncryst=16, steps=None):
-    """The reference's CPU path (oracle restatement of DiffCSPModule.sample, all host threads) on a bounded
-    sample: the first `ncryst` crystals of the workload, `steps` of the 1000 reverse steps; every step costs
-    the same (2 forwards), so crystals/s for 1000 steps is extrapolated linearly."""
+WORKLOAD = "DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU"
+
+
+def reference_module(timesteps, device="cpu"):
+    """the UNMODIFIED reference DiffCSPModule (full-size net, same seeded weights as build_model) from /root/reference or
+    the staged baseline/_ref copy; None when neither exists"""
     from oracle import diffcsp_oracle as O
+    from oracle import ref_import as R
+    if not R.reference_available():
+        return None
+    hp = O.default_hparams(timesteps=timesteps)
+    torch.manual_seed(1234)
+    ref = R.build_reference_module(hp, sigmas_norm() if timesteps == HP["timesteps"] else None)
+    ref.decoder.load_state_dict(O.init_params(hp, seed=0, head_scale=HEAD_SCALE))
+    return ref.to(device).eval()
+
+
+def cpu_reference_leg(na_all, state_dict=None, seconds_target=20.0, ncryst=64, steps=None):
+    """The reference's CPU path on a bounded sample of the workload, all host threads: the first `ncryst` crystals,
+    `steps` reverse steps (a complete DiffCSPModule.sample of a `steps`-step schedule: every reverse step costs the same —
+    2 score-network evaluations + the update — so crystals/s for 1000 steps is steps-for-steps proportional).
+    kind = "reference": the unmodified reference module; "port": the oracle restatement (only where no reference copy exists)."""
+    from oracle import diffcsp_oracle as O
+    from oracle.ref_import import make_batch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    hp = O.default_hparams()
-    sch = O.Schedules(hp, sigmas_norm())
-    na = na_all[:ncryst]
-    sd = {k: v.detach().cpu().float() for k, v in state_dict.items()}
-    noise = O.Noise(torch.Generator().manual_seed(0))
-    with torch.no_grad():
+    na = [max(1, n) for n in na_all[:ncryst]]
+    probe = reference_module(2)
+    kind = "reference" if probe is not None else "port"
+
+    def run(T):
+        if kind == "reference":
+            ref = probe if T == 2 else reference_module(T)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                ref.sample(make_batch(na), step_lr=STEP_LR)
+            return time.perf_counter() - t0
+        hp = O.default_hparams()
+        sd = state_dict if state_dict is not None else O.init_params(hp, seed=0, head_scale=HEAD_SCALE)
+        sd = {k: v.detach().cpu().float() for k, v in sd.items()}
         t0 = time.perf_counter()
-        O.sample(sd, hp, sch, na, noise, step_lr=STEP_LR, timesteps=2)
-        per_step = (time.perf_counter() - t0) / 2
-        if steps is None:
-            steps = int(max(4, min(200, seconds_target / max(per_step, 1e-3))))
-        t0 = time.perf_counter()
-        O.sample(sd, hp, sch, na, noise, step_lr=STEP_LR, timesteps=steps)
-        dt = time.perf_counter() - t0
+        with torch.no_grad():
+            O.sample(sd, hp, O.Schedules(hp, sigmas_norm()), na, O.Noise(torch.Generator().manual_seed(0)), step_lr=STEP_LR, timesteps=T)
+        return time.perf_counter() - t0
+
+    per_step = run(2) / 2
+    if steps is None:
+        steps = int(max(4, min(200, seconds_target / max(per_step, 1e-3))))
+    dt = run(steps)
     value = len(na) / (dt / steps * HP["timesteps"])
-    return dict(value=value, unit="crystals/s", cores=cores, kind="port",
-                sample="first %d crystals of the workload, %d of 1000 reverse steps in %.1f s, extrapolated x%d"
-                       % (len(na), steps, dt, HP["timesteps"] // steps if steps else 0)), dt / steps
+    return dict(value=value, unit="crystals/s", cores=cores, kind=kind,
+                sample="%s DiffCSPModule.sample on the first %d crystals of the workload, %d reverse steps in %.1f s "
+                       "(per-step cost is t-independent: x%.0f to 1000 steps)"
+                       % ("unmodified reference" if kind == "reference" else "oracle port of", len(na), steps, dt,
+                          HP["timesteps"] / steps)), dt / steps
+
+
+def gpu_reference_leg(na, dev):
+    """Comparator B: the unmodified reference sampler on this GPU, the benchmark batch, all 1000 steps, timed once."""
+    from oracle.ref_import import make_batch
+    ref = reference_module(HP["timesteps"], dev)
+    if ref is None:
+        return dict(unavailable="no reference copy (run __graft_entry__.build() where /root/reference exists)")
+    batch = make_batch([max(1, n) for n in na])
+    batch.num_atoms, batch.batch = batch.num_atoms.to(dev), batch.batch.to(dev)
+    with torch.no_grad():
+        warm = reference_module(4, dev)
+        warm.sample(batch, step_lr=STEP_LR)                    # cuBLAS / allocator warm-up on a 4-step schedule
+        del warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, _ = ref.sample(batch, step_lr=STEP_LR)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    ok = bool(torch.isfinite(out["lattices"]).all())
+    del ref, out
+    torch.cuda.empty_cache()
+    return dict(value=len(na) / dt, unit="crystals/s", seconds=dt, crystals=len(na), reverse_steps=HP["timesteps"], finite=ok,
+                note="unmodified reference models/diffcsp/{diffusion,cspnet}.py on cuda (torch %s eager, fp32, TF32 off as "
+                     "at the reference's first sample_step), full 1000 steps, one pass" % torch.__version__)
 
 
 def run_reference(args):
@@ -145,12 +209,10 @@ def run_reference(args):
     if rank != 0:
         return
     na = atom_counts(args.batch)
-    from oracle import diffcsp_oracle as O
-    sd = O.init_params(O.default_hparams(), seed=0, head_scale=HEAD_SCALE)
     vals, ms = [], []
     total = args.warmup + args.steps
     for i in range(total):
-        cb, per_step = cpu_reference_leg(na, sd, seconds_target=max(3.0, 60.0 / total))
+        cb, per_step = cpu_reference_leg(na, seconds_target=max(3.0, 150.0 / total))
         if i >= args.warmup:
             vals.append(cb["value"])
             ms.append(per_step * 1e3)
@@ -160,9 +222,9 @@ def run_reference(args):
         metric="crystals/sec sampled (1000-step reverse)", value=v, unit="crystals/s", impl="reference",
         n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=float(np.mean(ms)) * HP["timesteps"],
         higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload="DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU" % args.batch,
-                    note="reference CPU path (oracle port; the Python reference cannot travel to the GPU box), "
-                         "bounded sample extrapolated to 1000 steps"),
+        config=dict(workload=WORKLOAD % args.batch,
+                    note="the reference's CPU implementation of the path on this box's host cores; every step is a bounded "
+                         "sample of the workload (cpu_baseline.sample)"),
         cpu_baseline=cb, e2e=dict(value=v, unit="crystals/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
@@ -172,7 +234,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="crystals per GPU (BASELINE configs[1])")
+    ap.add_argument("--batch", type=int, default=256, help="crystals per GPU (the batch size of BASELINE configs[1])")
+    ap.add_argument("--strong-batch", type=int, default=1024, help="global batch of the strong-scaling leg (BASELINE configs[2])")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-gpu-ref", action="store_true", help="skip Comparator B (the unmodified reference on this GPU)")
     ap.add_argument("--timesteps", type=int, default=None, help="debug: shorter reverse process (invalid as a bench value)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -205,8 +270,12 @@ def main():
     m = build_model(dev)
     m.decoder.use_tc = not args.ffma
     T = args.timesteps or HP["timesteps"]
+    from matinvent_b200.models.diffcsp.finetune import partition_crystals
     na_all = atom_counts(args.batch * world)
-    na = na_all[rank * args.batch:(rank + 1) * args.batch]          # weak scaling: fixed crystals per GPU
+    # weak scaling: `--batch` crystals per GPU on average; the shards are contiguous and balanced by sum n^2 (edges),
+    # so the max-over-ranks time measures the sampler, not the luck of the draw (a cut by count leaves +-12 % edges)
+    lo_, hi_ = partition_crystals(na_all, world)[rank]
+    na = na_all[lo_:hi_]
     batch = CrystalBatch([CrystalData(None, None, None, None, n) for n in na])
 
     def barrier():
@@ -239,7 +308,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
-    value = args.batch * world * args.steps / (ms / 1e3) * (HP["timesteps"] / T)
+    value = len(na_all) * args.steps / (ms / 1e3) * (HP["timesteps"] / T)
     assert torch.isfinite(out["lattices"]).all() and torch.isfinite(out["frac_coords"]).all()
 
     # ---- launches: count one eager reverse step, multiply (graph replays launch the same kernels)
@@ -267,10 +336,12 @@ def main():
         for i in range(HP["num_layers"]):
             q = "l%d." % i
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            if merged:
+                ws.cat[0][:, H:].zero_()          # destination of the fused scatter-mean (the layer's LayerNorm zeroes it in situ)
             e0.record()
             dec.edge_gemm1(i, ws, g, g.E, ws.a1[0], False, presplit, merged)
             e1.record()
-            dec.edge_gemm2(i, ws, g.E, ws.a1[0], False, merged)
+            dec.edge_gemm2(i, ws, g, g.E, ws.a1[0], ws.cat[0][:, H:], False, merged)
             e2.record()
             evs.append((e0, e1, e2))
     torch.cuda.synchronize()
@@ -306,7 +377,7 @@ def main():
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ops.segment_reduce(ws.a2, g.seg_ptr, ws.cat[0][:, H:], g.N, H, mean=True)
+        ops.segment_reduce(ws.a2, g.seg_ptr, ws.cat[0][:, H:], g.N, H, mean=True, rows=g.E)
         b.record()
         seg.append((a, b))
     torch.cuda.synchronize()
@@ -320,48 +391,76 @@ def main():
                             note="in isolation, L2 flushed between launches; 76 MB is ~2x the DRAM latency floor of a launch: the "
                                  "same kernel reaches 77 % at 4x the batch (scripts/bench_seg.py, profiles/README.md)")
 
+    # ---- strong scaling: a FIXED global batch (BASELINE configs[2]: 1024 crystals) sharded over the N GPUs
+    strong = None
+    if not args.no_strong and not args.timesteps:
+        na_s = atom_counts(args.strong_batch)
+        parts = partition_crystals(na_s, world)
+        slo, shi = parts[rank]
+        sbatch = CrystalBatch([CrystalData(None, None, None, None, n) for n in na_s[slo:shi]])
+        m.sample(sbatch, step_lr=STEP_LR, noise=PhiloxNoise(dev, seed=50))            # warm: workspace + graph capture
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_s = 2
+        a.record()
+        for k in range(n_s):
+            m.sample(sbatch, step_lr=STEP_LR, noise=PhiloxNoise(dev, seed=60 + k))
+        b.record()
+        barrier()
+        ts = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        e_rank = [sum(n * n for n in na_s[p:q]) for p, q in parts]
+        strong = dict(value=args.strong_batch * n_s / (float(ts) / 1e3), unit="crystals/s", global_batch=args.strong_batch,
+                      crystals_per_gpu=[q - p for p, q in parts], edges_per_gpu=e_rank, passes=n_s,
+                      ms_per_pass=float(ts) / n_s, scaling="strong",
+                      note="BASELINE configs[2]: fixed global batch sharded by sum n^2, no collective while sampling; "
+                           "speed-up over N = 1 is this value / the N = 1 line's strong_scaling.value")
+        m.decoder.release(m.decoder.graph_for(sbatch.num_atoms))
+
     # ---- e2e through the plugin call, host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        sampler = DiffCSPSampler(batch_size=args.batch, num_batches=1)
+        sampler = DiffCSPSampler(batch_size=len(na), num_batches=1)
         torch.manual_seed(1234 + rank)
+        gen_kw = {}
 
         def same_workload():
-            # generate() draws its atom counts from numpy's global RNG (sample.py:117-138): position the stream so that
-            # it draws exactly this rank's slice of the benchmark workload (atom_counts), i.e. the batch `value` ran
-            from matinvent_b200.models.diffcsp.sample import ATOM_DIST
+            # generate() draws its atom counts from numpy's global RNG (sample.py:117-138).  One GPU: seed the stream so
+            # that it draws exactly the benchmark workload (atom_counts); several GPUs: hand every rank its shard of that
+            # draw, which is what MatInvent.sample_step does
             np.random.seed(0)
-            if rank:
-                np.random.choice(21, rank * args.batch, p=ATOM_DIST["mp_20"])
+            if world > 1:
+                gen_kw["num_atoms"] = na
 
         if args.timesteps:
             e2e = None
         else:
             same_workload()
-            sampler.generate(m)                         # warm
+            sampler.generate(m, **gen_kw)               # warm
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             n_e2e = max(1, min(args.steps, 2))
             for _ in range(n_e2e):
                 same_workload()
-                data, _ = sampler.generate(m)
+                data, _ = sampler.generate(m, **gen_kw)
             b.record()
             barrier()
             t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             nn = sum(int(d.num_atoms) for d in data)
-            e2e = dict(value=args.batch * world * n_e2e / (float(t) / 1e3), unit="crystals/s",
-                       h2d_bytes_per_step=4 * (nn * 3 + args.batch * 9 + nn * 100),
-                       d2h_bytes_per_step=4 * (nn * 3 + nn + args.batch * 6), passes=n_e2e,
+            e2e = dict(value=len(na_all) * n_e2e / (float(t) / 1e3), unit="crystals/s",
+                       h2d_bytes_per_step=4 * (nn * 3 + len(na) * 9 + nn * 100),
+                       d2h_bytes_per_step=4 * (nn * 3 + nn + len(na) * 6), passes=n_e2e,
                        same_workload_as_value=bool(nn == g.N))
 
     # ---- second half of the hot path: the reward-weighted fine-tune step at the reference's working point
     # (<= 18 crystals, accum_steps 50), CUDA events around one epoch of 1000 timesteps as the pipeline runs
     # it: the first group of stacked timesteps eagerly, one CUDA-graph capture, 18 replays, 20 Adam steps
     ft = None
-    if world == 1 and not args.no_e2e and not args.timesteps:
+    if not args.no_e2e and not args.timesteps:
         from matinvent_b200.models.diffcsp.finetune import FineTuner
         prior = build_model(dev)
         for p_ in prior.parameters():
@@ -377,22 +476,59 @@ def main():
         fbatch = CrystalBatch(crystals)
         snap = m.decoder.flat.data.clone()
         try:      # a secondary figure: it must never cost the headline line
-            tuner = FineTuner(m, prior, lr=1e-4, accum_steps=50, sigma=0.025, noise=PhiloxNoise(dev, seed=3))
+            # every rank: same batch, same Philox seed (the noise is drawn for the GLOBAL batch and sliced), its own shard
+            tuner = FineTuner(m, prior, lr=1e-4, accum_steps=50, sigma=0.025, noise=PhiloxNoise(dev, seed=3), rank=rank, world=world)
             tuner.run_batch(fbatch, 100)                       # warm: allocations, kernel attributes
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             tuner.run_batch(fbatch, 1000)
             b.record()
-            torch.cuda.synchronize()
-            ft = dict(ms_per_timestep=a.elapsed_time(b) / 1000, crystals=len(nft), atoms=sum(nft), edges=sum(n * n for n in nft),
-                      timesteps_per_launch=tuner.group_size(sum(n * n for n in nft)), accum_steps=50,
-                      note="agent forward + prior forward + losses + backward per timestep, Adam every 50, one epoch of 1000 "
-                           "timesteps including its one CUDA-graph capture; the reference runs 3 such epochs per RL iteration")
+            barrier()
+            tf = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            parts = partition_crystals(nft, world)
+            ft = dict(ms_per_timestep=float(tf) / 1000, crystals=len(nft), atoms=sum(nft), edges=sum(n * n for n in nft),
+                      crystals_per_gpu=[q - p for p, q in parts],
+                      timesteps_per_launch=tuner.group_size(max(sum(n * n for n in nft[p:q]) for p, q in parts)), accum_steps=50,
+                      adam_steps_in_epoch=20, grad_bytes=4 * tuner.grad.numel(),
+                      note="agent forward + prior forward + losses + backward per timestep, every 50 timesteps ONE all-reduce of "
+                           "the flat gradient buffer (N > 1) + the flat Adam kernel; one epoch of 1000 timesteps including its "
+                           "CUDA-graph capture; max over ranks; the reference runs 3 such epochs per RL iteration")
+            if world > 1:      # the collective on its own: the 49 MB flat gradient buffer over NVLink
+                gbuf = tuner.grad
+                for _ in range(3):
+                    dist.all_reduce(gbuf)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(20):
+                    dist.all_reduce(gbuf)
+                b.record()
+                barrier()
+                ta = torch.tensor([a.elapsed_time(b) / 20], device=dev, dtype=torch.float64)
+                dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+                nb = 4 * gbuf.numel()
+                ft["allreduce_us"] = float(ta) * 1e3
+                ft["allreduce_bus_gbs"] = 2 * (world - 1) / world * nb / (float(ta) / 1e3) / 1e9
+                ft["allreduce_share_of_epoch"] = 20 * float(ta) / float(tf)
+                gbuf.zero_()
         except Exception as exc:      # noqa: BLE001
             ft = dict(error="%s: %s" % (type(exc).__name__, exc))
         finally:
             m.decoder.flat.data.copy_(snap)                    # the benchmark model is left as it was
             m.decoder.weights_changed()
+        del prior
+
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_gpu_ref and not args.timesteps and not args.no_cpu:
+        try:
+            gpu_ref = gpu_reference_leg(na_all, dev)
+            if "value" in gpu_ref:
+                gpu_ref["speedup_value_over_gpu_reference"] = value / gpu_ref["value"]
+        except Exception as exc:      # noqa: BLE001
+            gpu_ref = dict(error="%s: %s" % (type(exc).__name__, exc))
 
     cb = None
     if rank == 0 and not args.no_cpu:
@@ -403,15 +539,18 @@ def main():
             metric="crystals/sec sampled (1000-step reverse)", value=value, unit="crystals/s", n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload="DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU "
-                                 "(BASELINE configs[1])" % args.batch,
-                        crystals_per_gpu=args.batch, atoms_per_gpu=g.N, edges_per_gpu=g.E, reverse_steps=T,
+            config=dict(workload=WORKLOAD % args.batch,
+                        note="SURVEY.md §8(d) config (2): the DiffCSP back-end at the batch size of BASELINE configs[1]; the MatterGen "
+                             "configs are unmeasured (its score network lives in an un-vendored package)",
+                        crystals_per_gpu=len(na), atoms_per_gpu=g.N, edges_per_gpu=g.E, reverse_steps=T,
                         forwards_per_step=2, gflop_per_forward=flops_fwd / 1e9,
                         l2="per-step working set (weights 49 MB + Phi %d MB + 2x edge activations %d MB) exceeds the 126 MB L2; no flush"
                            % (4 * g.E * F6 >> 20, 2 * 4 * g.E * H >> 20),
-                        parallelism="dp%d (crystals sharded, no collective while sampling)" % world),
+                        parallelism="dp%d (crystals sharded by sum n^2, no collective while sampling; one gradient all-reduce per "
+                                    "Adam step while fine-tuning)" % world),
             clocks=clk, gpu_launches=gpu_launches, launches_per_reverse_step=per_step_launches,
-            e2e=e2e, fine_tune_step=ft, roofline=roofline, roofline_edge_scatter=roofline_scatter, cpu_baseline=cb)))
+            e2e=e2e, strong_scaling=strong, fine_tune_step=ft, roofline=roofline, roofline_edge_scatter=roofline_scatter,
+            cpu_baseline=cb, gpu_reference=gpu_ref)))
         sys.stdout.flush()
         os.write(json_fd, (line + "\n").encode())
     if world > 1:

@@ -67,6 +67,16 @@ typedef struct {
     const float* col_scale; /* optional [N], mi_tc_gemm only: the accumulator column n is multiplied by col_scale[n]
                              (together with alpha) before bias / gathers: undoes the per-row power-of-two scales
                              mi_f16_split_rows applied to W (mi_sgemm rejects it) */
+    /* Fused scatter-mean (mi_tc_gemm, MI_TC_MERGED, plain or z_out epilogue; mi_sgemm rejects it): instead of storing
+     * C, rows are reduced by segment:  scat_out[scat_idx[m]][n] += scat_w[m] * v(m, n)   for every row m.  Rows of one
+     * segment must be consecutive (CSR order over the destination), scat_w[m] = 1 / (rows in the segment of m) gives
+     * the mean of torch_scatter.scatter(reduce='mean') (models/diffcsp/cspnet.py:79); scat_out [S, scat_ld] must be
+     * zeroed by the caller; C may be NULL.  scat_amax (nullable, [S], zeroed by the caller) receives max |v| over the
+     * segment's rows and all columns: an upper bound of the row maximum of scat_out, usable as the next GEMM's a_amax. */
+    float* scat_out; int scat_ld;
+    const int* scat_idx;
+    const float* scat_w;
+    float* scat_amax;
 } mi_epilogue_t;
 
 int mi_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
@@ -106,6 +116,23 @@ int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo,
                         const void* W_lo, int ldw, float* C, int ldc, const mi_epilogue_t* epi, int flags,
                         mi_stream_t stream);
 
+/* The node-level chain of a CSPNet layer boundary in ONE launch (inference; hidden_dim H = 512): thread-block clusters of
+ * four CTAs own 128 rows each, phases separated by cluster barriers, intermediates through L2 (csrc/mi_node.cu):
+ *   phase 0  an1 = silu(agg W_b^T + R + bn1)        node_mlp.0 (cspnet.py:77-82); W_b = node_mlp.0.weight[:, H:] as fp16
+ *                                                   (hi, lo) with row stride ld_wb, R = LN(h) node_mlp.0.weight[:, :H]^T
+ *                                                   (third block of the previous [P'|Q|R] GEMM), amax_agg = row maxima of agg
+ *   phase 1  h   = h_in + silu(an1 W_2^T + bn2)     node_mlp.2 + residual (cspnet.py:82, 91); h may alias h_in
+ *   phase 2  pqr = LN(h; ln_g, ln_b) W_pqr^T + cb[node_graph]   the NEXT layer's LayerNorm and per-node GEMM, W_pqr [3H, H];
+ *            zero_out (nullable): H floats per row are zeroed (the next fused scatter-mean's destination; may alias agg)
+ * n_phases = 2 stops after phase 1 (last layer).  amax_an1 [M] must be zeroed by the caller.  Replaces four launches
+ * (mi_tc_gemm x3 + mi_layernorm_fwd_split) with the same arithmetic. */
+int mi_node_chain(int M, int H, int n_phases, const float* agg, int ld_agg, const float* amax_agg, const void* wb_hi,
+                  const void* wb_lo, int ld_wb, const float* bn1, const float* R, int ld_r, float* an1, float* amax_an1,
+                  const void* w2_hi, const void* w2_lo, const float* bn2, const float* h_in, int ld_hin, float* h, int ld_h,
+                  const float* ln_g,
+                  const float* ln_b, float ln_eps, const void* wpqr_hi, const void* wpqr_lo, const float* cb, int ld_cb,
+                  const int* node_graph, float* pqr, int ld_pqr, float* zero_out, int ld_zero, mi_stream_t stream);
+
 /* Transposes that put the weight-gradient GEMM dW[N_out, K_in] += dY^T X (a sum over tens of thousands of edge or node
  * rows) into the K-contiguous form of mi_tc_gemm: dY^T is its fp32 A operand (row maxima = column maxima of dY), X^T
  * its pre-split merged-format W operand with one power-of-two scale per row (= per column of X).
@@ -143,9 +170,12 @@ int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, co
  *   mean != 0: scale_s = 1 / max(count, 1) (torch_scatter.scatter(reduce='mean'), cspnet.py:79,281)
  *   mean == 0: plain sum.  accumulate != 0: out += result.
  * H must be a multiple of 4 and rows 16-byte aligned.  amax_out (nullable, [S]) receives max |out[s][:]|
- * (for the row rescaling of mi_tc_gemm).  This is the edge-scatter roofline kernel. */
+ * (for the row rescaling of mi_tc_gemm).  This is the edge-scatter roofline kernel.
+ * rows: ptr[S] (the total number of rows) when the caller knows it, else 0.  With perm == NULL and rows > 0 the
+ * streaming kernel runs: every block owns the segments that start inside its 32-row chunk, so blocks move equal bytes
+ * whatever the segment sizes (same summation order per segment, bit-identical results). */
 int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
-                      int S, int H, int mean, int accumulate, float* amax_out, mi_stream_t stream);
+                      int S, int H, int mean, int accumulate, float* amax_out, int rows, mi_stream_t stream);
 
 /* dX[e][:] = dOut[idx[e]][:] * (inv_count ? 1/max(cnt(idx[e]),1) : 1) * (z ? silu'(z[e][:]) : 1)
  * (backward of segment mean + SiLU).  idx nullable -> identity; ptr = CSR used for counts (nullable ->
@@ -161,6 +191,14 @@ int mi_colsum(const float* X, int ldx, int M, int N, float* out, int accumulate,
  * amax_out (nullable, [rows]): atomic max of |y[row][:]| (row rescaling of the tensor-core GEMM reading y) */
 int mi_layernorm_fwd(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
                      float* mean, float* rstd, int rows, int H, float eps, float* amax_out, mi_stream_t stream);
+/* LayerNorm feeding a tensor-core GEMM directly: y is written as the pre-split fp16 operand pair of
+ * mi_tc_gemm_presplit (flags = 0 format) scaled per row by the power of two that GEMM derives from epi->a_amax, which
+ * this call stores into amax [rows] (pass it as epi->a_amax: the GEMM then scales the result rows back).  y (fp32,
+ * nullable) is also written when given (training keeps it for the backward); zero_out (nullable): zero_cols floats per
+ * row are zeroed (the destination of the fused scatter-mean that follows in the layer).  H <= 1024. */
+int mi_layernorm_fwd_split(const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                           void* y_hi, void* y_lo, int ldh, float* amax, float* zero_out, int ldz, int zero_cols,
+                           float* mean, float* rstd, int rows, int H, float eps, mi_stream_t stream);
 /* dx (+)= LN backward; dgamma/dbeta += (atomics) */
 int mi_layernorm_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma,
                      const float* mean, const float* rstd, float* dx, int lddx, int accumulate_dx,
@@ -299,6 +337,11 @@ int mi_composition_reward(const int* Z, const int* node_off, int B, const double
                           const int* modes, const int* targets, const double* minv, const double* maxv,
                           const double* tval, const double* weight, int reduce, double* props, double* rewards,
                           int* failed, mi_stream_t stream);
+
+/* MatterGen adapter (models/mattergen/loss.py:63-73): out[b] = sum_k weights[k] * f_k[b] over F <= 4 per-field
+ * per-sample loss vectors, accumulated in the given order (weights: HOST array of F floats). */
+int mi_weighted_field_sum(int B, int F, const float* f0, const float* f1, const float* f2, const float* f3,
+                          const float* weights_host, float* out, mi_stream_t stream);
 
 #ifdef __cplusplus
 }

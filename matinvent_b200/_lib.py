@@ -20,7 +20,8 @@ class Epilogue(C.Structure):
                 ("z_in", c_fp), ("zin_ld", C.c_int),
                 ("resid", c_fp), ("resid_ld", C.c_int),
                 ("act", C.c_int), ("alpha", C.c_float), ("beta", C.c_float), ("splitk", C.c_int),
-                ("amax_out", c_fp), ("a_amax", c_fp), ("col_scale", c_fp)]
+                ("amax_out", c_fp), ("a_amax", c_fp), ("col_scale", c_fp),
+                ("scat_out", c_fp), ("scat_ld", C.c_int), ("scat_idx", c_fp), ("scat_w", c_fp), ("scat_amax", c_fp)]
 
 
 i, f, d, ll, u64, p = C.c_int, C.c_float, C.c_double, C.c_longlong, C.c_ulonglong, c_fp
@@ -36,12 +37,14 @@ PROTOTYPES = {
     "mi_transpose_split": [p, i, i, i, p, p, p, i, p, p],
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
+    "mi_node_chain": [i, i, i, p, i, p, p, p, i, p, p, i, p, p, p, p, p, p, i, p, i, p, p, f, p, p, p, i, p, p, i, p, i, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, f, f, p],
-    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
+    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, i, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p, p],
     "mi_colsum": [p, i, i, i, p, i, p],
     "mi_layernorm_fwd": [p, i, p, p, p, i, p, p, i, i, f, p, p],
+    "mi_layernorm_fwd_split": [p, i, p, p, p, i, p, p, i, p, p, i, i, p, p, i, i, f, p],
     "mi_layernorm_bwd": [p, i, p, i, p, p, p, p, i, i, p, p, i, i, p],
     "mi_lattice_ip": [p, p, i, p],
     "mi_lattice_linear": [p, p, p, p, i, i, i, i, ll, ll, ll, p],
@@ -64,6 +67,7 @@ PROTOTYPES = {
     "mi_build_dst_csr": [p, p, i, i, p, p, p, p],
     "mi_replay_select": [p, p, i, i, d, p, p, p],
     "mi_composition_key": [p, p, i, p, p],
+    "mi_weighted_field_sum": [i, i, p, p, p, p, C.POINTER(f), p, p],
     "mi_validity_prefilter": [p, p, p, p, i, f, f, f, f, p, p, p],
     "mi_composition_reward": [p, p, i, p, p, i, C.POINTER(i), C.POINTER(i), C.POINTER(d), C.POINTER(d), C.POINTER(d),
                               C.POINTER(d), i, p, p, p, p],

@@ -255,6 +255,7 @@ extern "C" int mi_sgemm(int transA, int transB, int M, int N, int K, const float
         p.e = z;
     }
     MI_CHECK_ARG(p.e.col_scale == nullptr, "col_scale belongs to the tensor-core path (mi_tc_gemm)");
+    MI_CHECK_ARG(p.e.scat_out == nullptr, "the fused scatter epilogue belongs to the tensor-core path (mi_tc_gemm)");
     if (p.e.splitk < 1) p.e.splitk = 1;
     if (p.e.splitk > 1) {
         MI_CHECK_ARG(!p.e.amax_out, "split-K cannot report row maxima");

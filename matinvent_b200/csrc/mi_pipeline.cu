@@ -184,3 +184,38 @@ extern "C" int mi_composition_reward(const int* Z, const int* node_off, int B, c
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------- MatterGen adapter
+// models/mattergen/loss.py:63-73: the per-sample loss is the weighted sum of the per-field per-sample losses
+// (pos 0.1, cell 1.0, atomic_numbers 1.0 by default), accumulated in the order the fields are given.
+namespace {
+struct FieldSum {
+    const float* f[4];
+    float w[4];
+    int F;
+};
+__global__ void weighted_field_sum_kernel(const FieldSum fs, int B, float* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float acc = fs.w[0] * fs.f[0][b];
+    for (int k = 1; k < fs.F; ++k) acc = acc + fs.w[k] * fs.f[k][b];
+    out[b] = acc;
+}
+}  // namespace
+
+extern "C" int mi_weighted_field_sum(int B, int F, const float* f0, const float* f1, const float* f2, const float* f3,
+                                     const float* weights_host, float* out, mi_stream_t stream) {
+    if (B <= 0) return MI_OK;
+    MI_CHECK_ARG(F >= 1 && F <= 4 && weights_host && out && f0, "1..4 fields");
+    FieldSum fs;
+    const float* f[4] = {f0, f1, f2, f3};
+    for (int k = 0; k < 4; ++k) {
+        fs.f[k] = f[k];
+        fs.w[k] = k < F ? weights_host[k] : 0.f;
+        MI_CHECK_ARG(k >= F || f[k] != nullptr, "null field");
+    }
+    fs.F = F;
+    weighted_field_sum_kernel<<<mi_div_up(B, 256), 256, 0, (cudaStream_t)stream>>>(fs, B, out);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}

@@ -28,7 +28,9 @@
 #include <stdlib.h>
 #include <cudaTypedefs.h>
 
-#include "mi_common.cuh"
+#include "mi_tc_common.cuh"
+
+using namespace mi_tc;
 
 namespace {
 
@@ -77,87 +79,6 @@ struct Cfg {
     static_assert(S >= 2 && SMEM_BYTES <= 232448 && TMEM_COLS <= 512, "configuration does not fit the SM");
     static_assert((3 * S + 2 * R + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
-constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-// K-major fp16 operand tile, 64-byte rows, SWIZZLE_64B: 8-row groups of 512 B (SBO), LBO unused (=1),
-// descriptor version 1, layout type 4.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// SiLU with ex2/rcp approximations (~3e-7 relative, below the GEMM's own error): 5 instructions instead of ~25,
-// the epilogue is issue/latency bound otherwise.
-// 16-byte read-only load that does not allocate in L1: the gathered rows are 4 KB apart (they thrash the L1 sets) and
-// every value is used once per CTA; reuse between CTAs is served by L2.
-__device__ __forceinline__ float4 ldg_stream4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// d/dx [x sigmoid(x)] = s (1 + x (1 - s)), same approximations
-__device__ __forceinline__ float dsilu_fast(float x) {
-    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
-    return s * fmaf(x, 1.0f - s, 1.0f);
-}
-// x -> (fp16(x), fp16((x - fp16(x)) * 2^11)) packed for two consecutive elements
-template <int MERGED>
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    __half2 h = __floats2half2_rn(x0, x1);
-    float2 hf = __half22float2(h);
-    const float ls = MERGED ? 1.0f : LO_SCALE;
-    __half2 l = __floats2half2_rn((x0 - hf.x) * ls, (x1 - hf.y) * ls);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-}
 
 #ifdef MI_TC_TRACE
 // Developer instrumentation (scripts/trace_tc.py builds a separate library with -DMI_TC_TRACE; never in the product
@@ -182,18 +103,29 @@ struct TcParams {
                   // reductions (weight gradients: few output tiles, tens of thousands of reduction rows)
 };
 
-// tcgen05.ld of a 32-lane x 32-column fp32 block (lane = row, registers = consecutive columns); completion is
-// only guaranteed after tcgen05.wait::ld.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
+// Segment sums of one 32x32 chunk held in a warp's transpose buffer (row-major, pitch EP): lane = column, the rows of
+// every segment are walked in order and one 128-byte reduction per (segment, chunk) goes to the zeroed destination.  A
+// segment (<= ~20 rows with fc edges) meets at most two 32-row windows, so every destination element receives at most
+// two partial sums: the result does not depend on their order.
+__device__ __forceinline__ void scatter_chunk(const float* ebuf, int EP, uint32_t starts, int my_seg, float my_w,
+                                              float* __restrict__ out, int ld, int nb, int lane) {
+    uint32_t m = starts;
+    while (m) {                                                  // warp-uniform
+        const int a = __ffs(m) - 1;
+        m &= m - 1;
+        const int b = m ? __ffs(m) - 1 : 32;
+        const int sg = __shfl_sync(0xffffffffu, my_seg, a);
+        const float wg = __shfl_sync(0xffffffffu, my_w, a);
+        if (sg < 0) break;                                       // rows past M
+        float s0 = 0.f, s1 = 0.f;
+        int rr = a;
+        for (; rr + 2 <= b; rr += 2) {
+            s0 += ebuf[rr * EP + lane];
+            s1 += ebuf[(rr + 1) * EP + lane];
+        }
+        if (rr < b) s0 += ebuf[rr * EP + lane];
+        atomicAdd(out + (long long)sg * ld + nb + lane, (s0 + s1) * wg);
+    }
 }
 
 // EPI bit 0: row gathers g1 / g2 present, bit 1: pre-activation store (training), bit 2: third gather g3 and / or
@@ -213,6 +145,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr int A_RAW = C::A_RAW, A_H = C::A_H, W_H = C::W_H, OPB = C::OPB, S = C::S, R = C::R;
     constexpr int RR = R > 0 ? R : 1;                     // divisor only
     extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
+#ifdef MI_TC_TRACE
+    if (threadIdx.x == 0) {                                // wall-clock (ns) at kernel entry: launch ramp vs in-kernel time
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_trace[(blockIdx.x * TR_TILES) * TR_SLOTS + 21] = (long long)gt;
+    }
+#endif
     uint8_t* raw_ring = smem;
     uint8_t* op_ring = smem + C::RAW_BYTES;
     float* ebuf_all = reinterpret_cast<float*>(smem + C::RAW_BYTES + C::OP_BYTES);      // EPI_WARPS x 32 x EPITCH floats
@@ -452,6 +391,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const bool mrow_ok = mrow < p.M;
                 i3 = (mrow_ok && e.g3) ? (e.g3_idx ? __ldg(e.g3_idx + mrow) : mrow) : 0;
             }
+            // fused scatter-mean (EPI bit 4): the segment (destination row of the reduction) and the weight 1 / count of
+            // the row this lane owns in TMEM; rows of one segment are consecutive
+            int my_seg = -1;
+            float my_w = 0.f;
+            if ((EPI & 16) && mrow < p.M) {
+                my_seg = __ldg(e.scat_idx + mrow);
+                my_w = __ldg(e.scat_w + mrow);
+            }
+            // bit r: row r of this warp's 32-row window starts a segment (row 0 always does); rows past M form a last
+            // "segment" with index -1 that is skipped
+            uint32_t seg_starts = 0;
+            float seg_rmax = 0.f;                                // max |v| of the row this lane owns, all columns (EPI == 16)
+            if (EPI & 16) {
+                const int prev = __shfl_up_sync(0xffffffffu, my_seg, 1);
+                seg_starts = __ballot_sync(0xffffffffu, lane == 0 || my_seg != prev);
+            }
             float rowmax[8];                                     // running max |C| of the 8 rows this lane touches
 #pragma unroll
             for (int u = 0; u < 8; ++u) rowmax[u] = 0.f;
@@ -496,6 +451,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                }
+                if (EPI == 16) {
+                    // inference form of the fused scatter: column scale, bias and SiLU are applied here, in the
+                    // row-per-lane layout TMEM delivers (the per-column constants are warp-uniform loads), the values go
+                    // through the transpose buffer once and are summed by segment: no second stage, no global store of C
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float2 cs2 = e.col_scale ? __ldg(reinterpret_cast<const float2*>(e.col_scale + nb + j)) : make_float2(1.f, 1.f);
+                            const float2 b2 = e.bias ? __ldg(reinterpret_cast<const float2*>(e.bias + nb + j)) : make_float2(0.f, 0.f);
+                            float y0 = fmaf(rowsc * __uint_as_float(v[j]), cs2.x, b2.x);
+                            float y1 = fmaf(rowsc * __uint_as_float(v[j + 1]), cs2.y, b2.y);
+                            if (e.act == MI_ACT_SILU) y0 = silu_fast(y0), y1 = silu_fast(y1);
+                            seg_rmax = fmaxf(seg_rmax, fmaxf(fabsf(y0), fabsf(y1)));
+                            *reinterpret_cast<float2*>(ebuf + lane * EP + j) = make_float2(y0, y1);
+                        }
+                    }
+                    __syncwarp();
+                    if (PREFETCH && cc + 1 < CH) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), v);
+                    if (live) scatter_chunk(ebuf, EP, seg_starts, my_seg, my_w, e.scat_out, e.scat_ld, nb, lane);
+                    __syncwarp();
+                    continue;
                 }
                 if (live) {
 #pragma unroll
@@ -560,7 +537,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             if (EPI & 4) { x[0] += gr[u].x; x[1] += gr[u].y; x[2] += gr[u].z; x[3] += gr[u].w; }
 #ifndef MI_TC_NOSTORE
-                            if (p.ksplit > 1)
+                            if (EPI & 16) {          // back into the transpose buffer (this lane's own slots): summed below
+                                const int rr = (hb * 4 + u) * 4 + (lane >> 3);
+                                *reinterpret_cast<float2*>(ebuf + rr * EP + col4) = make_float2(x[0], x[1]);
+                                *reinterpret_cast<float2*>(ebuf + rr * EP + col4 + 2) = make_float2(x[2], x[3]);
+                            } else if (p.ksplit > 1)
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C + (long long)m * p.ldc + n), "f"(x[0]),
                                              "f"(x[1]), "f"(x[2]), "f"(x[3])
                                              : "memory");
@@ -572,6 +553,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             rowmax[hb * 4 + u] = fmaxf(rowmax[hb * 4 + u], fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3]))));
                         }
                         if (threadIdx.x == 320 && cc == 0) TRACE(tl, 18 + 2 * hb);
+                    }
+                    if (EPI & 16) {
+                        __syncwarp();
+                        scatter_chunk(ebuf, EP, seg_starts, my_seg, my_w, e.scat_out, e.scat_ld, nb, lane);
                     }
                 } else if (live) {
                     // ---- generic path (ragged N or unaligned rows): scalar, bounds-checked
@@ -614,6 +599,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 __syncwarp();
                 if (threadIdx.x == 320 && cc < 4) TRACE(tl, 9 + cc);
             }
+            if ((EPI & 16) && e.scat_amax) {
+                // max |v| over the rows of a segment and all columns: an upper bound of the row maximum of the means
+                if (EPI == 16) {
+                    if (my_seg >= 0) atomicMax(reinterpret_cast<unsigned*>(e.scat_amax + my_seg), __float_as_uint(seg_rmax));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float rmax = rowmax[u];
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 1));
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 2));
+                        rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, 4));
+                        const int sg = __shfl_sync(0xffffffffu, my_seg, u * 4 + (lane >> 3));
+                        if ((lane & 7) == 0 && sg >= 0) atomicMax(reinterpret_cast<unsigned*>(e.scat_amax + sg), __float_as_uint(rmax));
+                    }
+                }
+            }
             if (e.amax_out) {                                    // one atomic per row per warp: max over the 8 lanes sharing a row
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -634,6 +635,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+#ifdef MI_TC_TRACE
+    if (threadIdx.x == 32) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_trace[(blockIdx.x * TR_TILES) * TR_SLOTS + 22] = (long long)gt;
+    }
+#endif
 }
 
 __global__ void f16_split_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, long long n,
@@ -753,7 +761,19 @@ int dispatch_tc(int epi_mode, bool presplit, int M, int N, int K, const void* A,
 #undef MI_TC_CASE
 }
 
+// fused scatter-mean epilogue (EPI bit 4): the second per-edge block only — merged 128x256 tiles, A split in the kernel
+int dispatch_tc_scatter(int epi_mode, int M, int N, int K, const void* A, int lda, const void* W_hi, const void* W_lo, int ldw,
+                        cudaStream_t s, const TcParams& p) {
+    if (epi_mode == 16) return launch_tc<256, 16, 1, 0>(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, s, p);
+    return launch_tc<256, 18, 1, 0>(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, s, p);
+}
+
 }  // namespace
+
+int mi_tc_get_encode() { return get_encode(); }
+int mi_tc_make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, bool half) {
+    return make_map(map, base, rows, cols, ld, box_rows, half);
+}
 
 #ifdef MI_TC_TRACE
 extern "C" int mi_tc_trace_read(long long* out, int n) {
@@ -785,7 +805,8 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     const bool merged = (flags & MI_TC_MERGED) != 0;
     MI_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "bad dimension");
     if (M == 0 || N == 0) return MI_OK;
-    MI_CHECK_ARG(A && W_hi && W_lo && C, "null operand");
+    const bool scat = epi && epi->scat_out != nullptr;
+    MI_CHECK_ARG(A && W_hi && W_lo && (C || scat), "null operand");
     MI_CHECK_ARG(lda >= K && ldw >= K && ldc >= N, "leading dimension too small");
     MI_CHECK_ARG(lda % (A_lo ? 8 : 4) == 0 && ldw % 8 == 0 && mi_host_aligned16(A) && (!A_lo || mi_host_aligned16(A_lo)) &&
                  mi_host_aligned16(W_hi) && mi_host_aligned16(W_lo), "TMA operands need 16-byte aligned rows (fp32: ld % 4, fp16: ld % 8)");
@@ -807,7 +828,7 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     if (p.e.act == MI_ACT_DSILU)
         MI_CHECK_ARG(p.e.z_in && !p.e.g1 && !p.e.g2 && !p.e.g3 && !p.e.z_out && !p.e.resid,
                      "MI_ACT_DSILU on the tensor-core path needs z_in and a plain epilogue otherwise");
-    bool cv = (ldc % 4 == 0) && mi_host_aligned16(C);
+    bool cv = scat || ((ldc % 4 == 0) && mi_host_aligned16(C));
     const mi_epilogue_t& e = p.e;
     if (e.bias) cv = cv && mi_host_aligned16(e.bias);
     if (e.g1) cv = cv && (e.g1_ld % 4 == 0) && mi_host_aligned16(e.g1);
@@ -819,7 +840,8 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     if (e.col_scale) cv = cv && mi_host_aligned16(e.col_scale);
     p.c_vec = cv;
     p.presplit = A_lo != nullptr;
-    if (p.presplit) MI_CHECK_ARG(p.e.a_amax == nullptr, "pre-split A carries no row rescaling");
+    // pre-split A with a_amax: the producer already scaled the rows by the power of two a_amax calls for
+    // (mi_layernorm_fwd_split); the epilogue scales the result rows back
     if (merged) MI_CHECK_ARG(p.presplit || p.e.a_amax != nullptr, "the merged format needs the row maxima of A (epi->a_amax)");
     // Column-tile width: 128 (two double-buffered {main, correction} accumulator pairs fill the 512 TMEM columns);
     // 64 only for narrow outputs.
@@ -828,6 +850,14 @@ static int tc_gemm_impl(int M, int N, int K, const void* A, const void* A_lo, in
     if (force) tn = atoi(force) <= 64 ? 64 : 128;
     cudaStream_t s = (cudaStream_t)stream;
     const int epi_mode = p.e.act == MI_ACT_DSILU ? 8 : (((p.e.g1 || p.e.g2) ? 1 : 0) | (p.e.z_out ? 2 : 0) | ((p.e.g3 || p.e.resid) ? 4 : 0));
+    if (scat) {
+        // the rows of C are not stored: segment means go to scat_out (zeroed by the caller), see mi_epilogue_t
+        MI_CHECK_ARG(merged && !p.presplit && (epi_mode & ~2) == 0 && p.ksplit == 1 && !p.e.amax_out,
+                     "the fused scatter epilogue exists for the merged, in-kernel-split format with a plain / z_out epilogue");
+        MI_CHECK_ARG(p.e.scat_idx && p.e.scat_w && N % 32 == 0 && p.c_vec && p.e.scat_ld >= N,
+                     "fused scatter: scat_idx / scat_w required, N % 32 == 0, 16-byte aligned epilogue operands");
+        return dispatch_tc_scatter(16 | epi_mode, M, N, K, A, lda, W_hi, W_lo, ldw, (cudaStream_t)stream, p);
+    }
     if (merged) return dispatch_tc<256, 1>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
     if (tn == 128) return dispatch_tc<128, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);
     return dispatch_tc<64, 0>(epi_mode, p.presplit != 0, M, N, K, A, A_lo, lda, W_hi, W_lo, ldw, s, p);

@@ -52,13 +52,19 @@ class _Workspace:
         self.tb = buf(B, H)
         # [C_b | 0] of every layer: folded into P by the P|Q GEMM's epilogue (one launch fills all layers: the lattices
         # do not change inside a forward)
-        self.cb2 = torch.zeros(net.num_layers, B, 2 * H, device=dev, dtype=f32)
+        self.cb = torch.zeros(net.num_layers, B, 3 * H, device=dev, dtype=f32)
+        self.cb2 = self.cb[:, :, :2 * H]
         self.h0 = buf(N, H)
         # inference: the embedding output keeps its own buffer (the predictor forward of a reverse step reuses the
         # corrector's: same atom-type state, time and lattice), the layers update one shared buffer in place
         self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] + [buf(N, H)] * L
         self.cat = [buf(N, 2 * H) for _ in range(nl)]
-        self.pq = buf(N, 2 * H)
+        # [P' | Q | R]: the per-node parts of the first edge linear and, third block, the LN(h) half of node_mlp.0
+        # (forward_graph, "node path"); the FP32 / unfused path uses the first two blocks only
+        self.pqr = buf(N, 3 * H)
+        self.pq = self.pqr[:, :2 * H]
+        self.hn_hi = torch.empty(N, H, device=dev, dtype=torch.float16)      # LN(h) as a pre-split tensor-core operand
+        self.hn_lo = torch.empty(N, H, device=dev, dtype=torch.float16)
         self.a1 = [buf(E, H) for _ in range(nl)]
         self.a2 = buf(E, H)
         self.an1 = [buf(N, H) for _ in range(nl)]
@@ -70,14 +76,15 @@ class _Workspace:
         self.pred_a = buf(N, A)
         # row-wise max |.| of the activations that feed tensor-core GEMMs (power-of-two row rescaling keeps the
         # fp16 split path inside fp32 dynamic range); zeroed at the start of every forward
-        self.amax = torch.zeros(N + L * (E + 2 * N), device=dev, dtype=f32)
+        self.amax = torch.zeros(N + L * (E + 3 * N), device=dev, dtype=f32)
         self.amax_h0 = self.amax[:N]
         o = N
-        self.amax_a1, self.amax_agg, self.amax_an1 = [], [], []
+        self.amax_a1, self.amax_agg, self.amax_an1, self.amax_hn = [], [], [], []
         for _ in range(L):
             self.amax_a1.append(self.amax[o:o + E]); o += E
             self.amax_agg.append(self.amax[o:o + N]); o += N
             self.amax_an1.append(self.amax[o:o + N]); o += N
+            self.amax_hn.append(self.amax[o:o + N]); o += N
         if train:
             self.z1 = [buf(E, H) for _ in range(L)]
             self.z2 = [buf(E, H) for _ in range(L)]
@@ -128,6 +135,10 @@ class _Workspace:
         return sc
 
 
+def an1_contig(ws):
+    return ws.an1[0].is_contiguous()
+
+
 class CSPNet(nn.Module):
     def __init__(self, hidden_dim=128, latent_dim=256, num_layers=4, max_atoms=100, act_fn="silu",
                  dis_emb="sin", num_freqs=10, edge_style="fc", cutoff=6.0, max_neighbors=20, ln=False,
@@ -172,7 +183,9 @@ class CSPNet(nn.Module):
         # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
+        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
+        self._pqr_hi, self._pqr_lo = {}, {}
         # transposed copies W^T (fp16 head / tail) of the weights whose input gradients run on the tensor cores
         # (dX = dY W is the forward kernel with W^T as its weight); built once a backward has asked for them
         self._hiT, self._loT, self._wT = {}, {}, {}
@@ -196,6 +209,7 @@ class CSPNet(nn.Module):
         self._ws, self._graphs = {}, {}
         self._flat_hi = self._flat_lo = None
         self._mhi, self._mlo, self._minv = {}, {}, {}
+        self._pqr_hi, self._pqr_lo = {}, {}
         self._hiT, self._loT, self._wT = {}, {}, {}
         self._tc_version = None
         return r
@@ -226,6 +240,17 @@ class CSPNet(nn.Module):
                         self._mlo[k] = torch.empty_like(w, dtype=torch.float16)
                         self._minv[k] = torch.empty(w.shape[0], device=w.device, dtype=torch.float32)
                     ops.f16_split_rows(w, self._mhi[k], self._mlo[k], self._minv[k])
+        # packed [W_hi; W_hj; node_mlp.0[:, :H]] rows (fp16 head / tail) of every layer: one per-node GEMM produces P, Q and
+        # the LN(h) half of node_mlp.0 (forward_graph, node path)
+        H = self.hidden_dim
+        for i in range(self.num_layers):
+            q = "l%d." % i
+            if i not in self._pqr_hi:
+                self._pqr_hi[i] = torch.empty(3 * H, H, device=self.flat.device, dtype=torch.float16)
+                self._pqr_lo[i] = torch.empty(3 * H, H, device=self.flat.device, dtype=torch.float16)
+            for dst, src in ((self._pqr_hi[i], self._hi), (self._pqr_lo[i], self._lo)):
+                dst[:2 * H].copy_(src[q + "w_pq"])
+                dst[2 * H:].copy_(src[q + "wn1"][:, :H])
         if self._need_T:
             for i in range(self.num_layers):
                 for k in ("l%d.wn2" % i, "l%d.wn1" % i, "l%d.w2" % i, "l%d.w_pq" % i):
@@ -244,6 +269,10 @@ class CSPNet(nn.Module):
         if self.use_tc and ops.tc_ok(A, self._hi[wname]):
             return ops.tc_gemm(A, self._hi[wname], self._lo[wname], C, M=M, **epi)
         return ops.sgemm(A, W, C, M=M, **epi)
+
+    def tc_linear_view(self, A, wname, cols, C, M, **epi):
+        """C = epilogue(A @ W[:, cols]^T) on the tensor cores (a column block of a weight: K = len(cols))"""
+        return ops.tc_gemm(A, self._hi[wname][:, cols], self._lo[wname][:, cols], C, M=M, **epi)
 
     def _dgrad(self, dY, wname, C, M, a_amax, act=ACT_NONE, z_in=None, amax_out=None, accumulate=False):
         """C = dY @ W (* silu'(z_in)) (+ C): input gradient of y = x W^T.  Tensor cores (the forward kernel with W^T as
@@ -447,15 +476,18 @@ class CSPNet(nn.Module):
         else:
             self._linear(ws.phi, q + "w_f", a1, E, **epi1)
 
-    def edge_gemm2(self, i, ws, E, a1, train, merged):
-        """a2 = silu(a1 W_2^T + b_2)   (second edge linear, cspnet.py:73-75)"""
-        q = "l%d." % i
+    def edge_gemm2(self, i, ws, g, E, a1, agg, train, merged):
+        """agg = mean_j silu(a1 W_2^T + b_2)   (second edge linear + scatter-mean over the source node, cspnet.py:73-79).
+        Merged tiles: the segment means are formed in the GEMM's epilogue (`agg` must be zeroed: the LayerNorm of the
+        layer does it) and the [E, H] messages are never written; otherwise GEMM -> a2 -> segment_reduce."""
+        N, H, q = g.N, self.hidden_dim, "l%d." % i
         epi2 = dict(bias=self._views[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU, a_amax=ws.amax_a1[i])
         if merged:
-            ops.tc_gemm(a1, self._mhi[q + "w2"], self._mlo[q + "w2"], ws.a2, M=E, col_scale=self._minv[q + "w2"],
-                        flags=ops.TC_MERGED, **epi2)
+            ops.tc_gemm(a1, self._mhi[q + "w2"], self._mlo[q + "w2"], None, M=E, col_scale=self._minv[q + "w2"],
+                        flags=ops.TC_MERGED, scatter=(agg, g.edge_src, g.edge_w, ws.amax_agg[i]), **epi2)
         else:
             self._linear(a1, q + "w2", ws.a2, E, **epi2)
+            ops.segment_reduce(ws.a2, g.seg_ptr, agg, N, H, mean=True, amax_out=ws.amax_agg[i], rows=E)
 
     # ------------------------------------------------------------------ forward
     def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None, reuse_embedding=False):
@@ -489,35 +521,71 @@ class CSPNet(nn.Module):
         # buffer are equally spaced)
         if not reuse:
             lstride = (self._slices["l1.w_l"][0] - self._slices["l0.w_l"][0]) if L > 1 else 0
-            ops.lattice_linear(l, W["l0.w_l"], W["l0.b1"], ws.cb2[0, :, :H], B, H, n_sets=L, w_stride=lstride,
-                               bias_stride=lstride, out_stride=ws.cb2.stride(0))
+            ops.lattice_linear(l, W["l0.w_l"], W["l0.b1"], ws.cb[0, :, :H], B, H, n_sets=L, w_stride=lstride,
+                               bias_stride=lstride, out_stride=ws.cb.stride(0))
+        # node path: LayerNorm emits the pre-split operand of ONE per-node GEMM that produces P', Q and R = LN(h) W_a^T
+        # (the LN(h) half of node_mlp.0, whose weight is [W_a | W_b] over [LN(h) | agg]); node_mlp.0 then runs on agg alone
+        # (K = H instead of 2H) and adds R in its epilogue.  Needs the tensor-core path and LayerNorm.
+        node_path = self.use_tc and self.ln and H % 8 == 0 and H <= 1024 and ops.tc_ok(ws.cat[0][:, H:], self._hi["l0.wn1"][:, H:])
+        # inference: the node-level chain of every layer boundary (node_mlp.0 -> node_mlp.2 + residual -> next layer's
+        # LayerNorm -> next P|Q|R GEMM) is ONE cluster launch (csrc/mi_node.cu) instead of four latency-bound ones
+        chain = node_path and not train and H == 512 and self.use_chain and an1_contig(ws)
         for i in range(L):
             q = "l%d." % i
             k = i if train else 0
             cat, a1, an1 = ws.cat[k], ws.a1[k], ws.an1[k]
             h_in, h_out = ws.h[i], ws.h[i + 1]
-            hn = cat[:, :H]
-            if self.ln:
-                # the row maximum of cat = [LN(h) | agg] is accumulated by both producers (LayerNorm here, the scatter below)
-                ops.layernorm_fwd(h_in, W[q + "ln_g"], W[q + "ln_b"], hn, N, H,
-                                  ws.ln_mean[i] if train else None, ws.ln_rstd[i] if train else None,
-                                  amax_out=ws.amax_agg[i])
+            hn, agg = cat[:, :H], cat[:, H:]
+            if chain:
+                if i == 0:
+                    ops.layernorm_fwd_split(h_in, W[q + "ln_g"], W[q + "ln_b"], None, ws.hn_hi, ws.hn_lo, ws.amax_hn[i], N, H,
+                                            zero_out=agg if merged else None, zero_cols=H)
+                    ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr, M=N,
+                                         gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i])
+                self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
+                self.edge_gemm2(i, ws, g, E, a1, agg, train, merged)
+                nxt = None
+                if i + 1 < L:
+                    qn = "l%d." % (i + 1)
+                    nxt = (W[qn + "ln_g"], W[qn + "ln_b"], 1e-5, self._pqr_hi[i + 1], self._pqr_lo[i + 1], ws.cb[i + 1],
+                           g.node_graph, ws.pqr)
+                ops.node_chain(N, H, agg, ws.amax_agg[i], self._hi[q + "wn1"][:, H:], self._lo[q + "wn1"][:, H:], W[q + "bn1"],
+                               ws.pqr[:, 2 * H:], an1, ws.amax_an1[i], self._hi[q + "wn2"], self._lo[q + "wn2"], W[q + "bn2"],
+                               h_in, h_out, ln=nxt, zero_out=agg)
+                continue
+            # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts; the
+            # per-crystal term C_b is folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the per-edge
+            # GEMM then adds two gathered rows instead of three
+            if node_path:
+                ops.layernorm_fwd_split(h_in, W[q + "ln_g"], W[q + "ln_b"], hn if train else None, ws.hn_hi, ws.hn_lo,
+                                        ws.amax_hn[i], N, H, zero_out=agg if merged else None, zero_cols=H,
+                                        mean=ws.ln_mean[i] if train else None, rstd=ws.ln_rstd[i] if train else None)
+                ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr, M=N,
+                                     gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i])
             else:
-                hn.copy_(h_in)
-                torch.maximum(ws.amax_agg[i], h_in.abs().amax(dim=1), out=ws.amax_agg[i])
-            # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts
-            # per-crystal term C_b first, folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the
-            # per-edge GEMM then adds two gathered rows instead of three
-            # (amax_agg[i] holds the row maxima of LN(h) only at this point: the scatter adds its own further down)
-            self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2[i], g.node_graph)],
-                         a_amax=ws.amax_agg[i])
+                if self.ln:
+                    # the row maximum of cat = [LN(h) | agg] is accumulated by both producers (LayerNorm here, the scatter below)
+                    ops.layernorm_fwd(h_in, W[q + "ln_g"], W[q + "ln_b"], hn, N, H,
+                                      ws.ln_mean[i] if train else None, ws.ln_rstd[i] if train else None,
+                                      amax_out=ws.amax_agg[i])
+                else:
+                    hn.copy_(h_in)
+                    torch.maximum(ws.amax_agg[i], h_in.abs().amax(dim=1), out=ws.amax_agg[i])
+                if merged:
+                    agg.zero_()
+                # (amax_agg[i] holds the row maxima of LN(h) only at this point: the scatter adds its own further down)
+                self._linear(hn, q + "w_pq", ws.pq, N, gathers=[(ws.cb2[i], g.node_graph)], a_amax=ws.amax_agg[i])
             self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
-            self.edge_gemm2(i, ws, E, a1, train, merged)
-            # scatter-mean over the source node (cspnet.py:79)
-            ops.segment_reduce(ws.a2, g.seg_ptr, cat[:, H:], N, H, mean=True, amax_out=ws.amax_agg[i])
+            # second edge linear + scatter-mean over the source node (cspnet.py:73-79)
+            self.edge_gemm2(i, ws, g, E, a1, agg, train, merged)
             # node model + residual (cspnet.py:77-91)
-            self._linear(cat, q + "wn1", an1, N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU,
-                         a_amax=ws.amax_agg[i], amax_out=ws.amax_an1[i])
+            if node_path:
+                self.tc_linear_view(agg, q + "wn1", slice(H, 2 * H), an1, N, bias=W[q + "bn1"], gathers=[(ws.pqr[:, 2 * H:], None)],
+                                    z_out=ws.zn1[i] if train else None, act=ACT_SILU, a_amax=ws.amax_agg[i],
+                                    amax_out=ws.amax_an1[i])
+            else:
+                self._linear(cat, q + "wn1", an1, N, bias=W[q + "bn1"], z_out=ws.zn1[i] if train else None, act=ACT_SILU,
+                             a_amax=ws.amax_agg[i], amax_out=ws.amax_an1[i])
             self._linear(an1, q + "wn2", h_out, N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
                          act=ACT_SILU, resid=h_in, a_amax=ws.amax_an1[i])
         hL = ws.h[L]
@@ -531,7 +599,7 @@ class CSPNet(nn.Module):
         if heads[1]:
             self._linear(hf, "coord_w", ws.pred_x, N)
         if heads[0]:
-            ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True)
+            ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True, rows=N)
             if self.ip:
                 self._linear(ws.gmean, "lattice_w", ws.lat9, B)
                 ops.bmm3(ws.lat9, l, ws.pred_l, B)
@@ -641,10 +709,10 @@ class CSPNet(nn.Module):
             # a1 = silu(z1) ; z1 = Phi w_f^T + P[src] + Q[dst] + C[graph]
             self._dgrad(ws.dz2, q + "w2", ws.dz1, E, ws.amax_dz2[i], act=ACT_DSILU, z_in=ws.z1[i])
             self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E, ws=ws, xt=phi_t)
-            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i])
+            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i], rows=E)
             ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False,
                                amax_out=ws.amax_dpq[i])
-            ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False)
+            ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False, rows=N)
             ops.colsum(ws.dcb, B, H, G[q + "b1"])
             self._wgrad(ws.dcb, ws.ips, q + "w_l", H, 9, B)
             self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N, ws=ws)
@@ -657,7 +725,7 @@ class CSPNet(nn.Module):
                 dh.add_(ws.dcat[:, :H])
         # ---- embedding
         self._wgrad(dh, ws.h0, "lat_w_h", H, H, N)
-        ops.segment_reduce(dh, g.node_off, ws.dtb, B, H, mean=False)
+        ops.segment_reduce(dh, g.node_off, ws.dtb, B, H, mean=False, rows=N)
         ops.colsum(ws.dtb, B, H, G["lat_b"])
         self._wgrad(ws.dtb, temb, "lat_w_t", H, T, B)
         ops.sgemm(dh, W["lat_w_h"], ws.dzn, transB=False, M=N, N=H, K=H)

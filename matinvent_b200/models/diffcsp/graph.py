@@ -45,6 +45,13 @@ class CrystalGraph:
         self.cell_off = None                                   # 'knn' only
         ops.fc_edges(self.node_off, self.edge_off, self.B, self.N, self.E, self.edge_src, self.edge_dst,
                      self.edge_graph, self.seg_ptr, self.dst_ptr, self.dst_perm, self.node_graph)
+        self.edge_w = self.mean_weights(self.E)
+
+    def mean_weights(self, E):
+        """edge_w[e] = 1 / (edges of the source node of e): the weights of the scatter-mean fused into the second
+        per-edge GEMM's epilogue (index table of the batch topology, built with it)"""
+        deg = (self.seg_ptr[1:] - self.seg_ptr[:-1]).clamp(min=1).to(torch.float32)
+        return (1.0 / deg)[self.edge_src[:E].long()].contiguous()
 
     @property
     def node2graph(self):

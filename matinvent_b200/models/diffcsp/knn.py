@@ -42,6 +42,7 @@ class KnnGraph(CrystalGraph):
         if tail[1]:
             raise RuntimeError("knn neighbour list overflow: a node has more than %d symmetric edges" % self.cap)
         self.E = int(tail[0])
+        self.edge_w = self.mean_weights(self.E)
         if need_dst:
             ops.build_dst_csr(self.seg_ptr, self.edge_dst, self.N, self.E_cap, self.dst_ptr, self.dst_perm, self._work)
         return self

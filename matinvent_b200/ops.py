@@ -63,8 +63,13 @@ def sgemm(A, B, C_, transA=False, transB=True, M=None, N=None, K=None, bias=None
     return C_
 
 
-def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out=None, a_amax=None, col_scale=None):
+def _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out=None, a_amax=None, col_scale=None,
+              scatter=None):
     e = Epilogue()
+    if scatter is not None:          # (out [S, >= N], idx [M] int32, weight [M], amax [S] or None)
+        so, si, sw, sa = scatter
+        _f32(so), _i32(si), _f32(sw), _f32(sa)
+        e.scat_out, e.scat_ld, e.scat_idx, e.scat_w, e.scat_amax = _p(so), _ld(so), _p(si), _p(sw), _p(sa)
     _f32(amax_out), _f32(a_amax), _f32(col_scale)
     e.amax_out, e.a_amax, e.col_scale = _p(amax_out), _p(a_amax), _p(col_scale)
     e.bias = _p(bias)
@@ -151,29 +156,31 @@ def tc_ok(A, W):
 
 
 def tc_gemm(A, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, z_in=None, resid=None,
-            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0, col_scale=None, splitk=1):
+            act=ACT_NONE, alpha=1.0, beta=0.0, amax_out=None, a_amax=None, flags=0, col_scale=None, splitk=1, scatter=None):
     """C = epilogue(alpha * A @ W^T) on the tensor cores (split FP16); W_hi/W_lo from f16_split.  See mi_tc_gemm.
-    splitk > 1: C += alpha * A @ W^T with K cut into splitk parts (plain epilogue only)."""
+    splitk > 1: C += alpha * A @ W^T with K cut into splitk parts (plain epilogue only).
+    scatter = (out, idx, weight, amax): rows are reduced by segment into `out` instead of being stored (C_ may be None)."""
     for t in (A, C_, bias, z_out, z_in, resid):
         _f32(t)
     M = A.shape[0] if M is None else M
     K = A.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out, a_amax, col_scale)
-    check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), C_.data_ptr(),
-                           _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm")
+    e = _epilogue(bias, gathers, z_out, z_in, resid, act, alpha, beta, splitk, amax_out, a_amax, col_scale, scatter)
+    check(lib().mi_tc_gemm(M, N, K, A.data_ptr(), _ld(A), W_hi.data_ptr(), W_lo.data_ptr(), _ld(W_hi), _p(C_),
+                           _ld(C_) if C_ is not None else N, C.byref(e), flags, _stream()), "mi_tc_gemm")
     return C_
 
 
 def tc_gemm_presplit(A_hi, A_lo, W_hi, W_lo, C_, M=None, N=None, K=None, bias=None, gathers=(), z_out=None, resid=None,
-                     act=ACT_NONE, alpha=1.0, amax_out=None, flags=0, col_scale=None):
-    """tc_gemm with A given as fp16 (hi, scaled lo) arrays from its producer.  See mi_tc_gemm_presplit."""
+                     act=ACT_NONE, alpha=1.0, amax_out=None, flags=0, col_scale=None, a_amax=None):
+    """tc_gemm with A given as fp16 (hi, scaled lo) arrays from its producer.  See mi_tc_gemm_presplit.
+    a_amax: the row maxima the producer scaled the rows by (layernorm_fwd_split): result rows are scaled back."""
     for t in (C_, bias, z_out, resid):
         _f32(t)
     M = A_hi.shape[0] if M is None else M
     K = A_hi.shape[1] if K is None else K
     N = W_hi.shape[0] if N is None else N
-    e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, None, col_scale)
+    e = _epilogue(bias, gathers, z_out, None, resid, act, alpha, 0.0, 1, amax_out, a_amax, col_scale)
     check(lib().mi_tc_gemm_presplit(M, N, K, A_hi.data_ptr(), A_lo.data_ptr(), _ld(A_hi), W_hi.data_ptr(), W_lo.data_ptr(),
                                     _ld(W_hi), C_.data_ptr(), _ld(C_), C.byref(e), flags, _stream()), "mi_tc_gemm_presplit")
     return C_
@@ -194,10 +201,11 @@ def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi, phi_hi=N
                                 ld, _p(phi_hi), _p(phi_lo), op_scale, lo_scale, _stream()), "mi_edge_fourier")
 
 
-def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None):
+def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None, rows=0):
+    """rows = ptr[S] when known on the host (selects the balanced streaming kernel for consecutive-row segments)"""
     _f32(X), _f32(out), _i32(ptr), _i32(perm), _f32(amax_out)
     check(lib().mi_segment_reduce(_p(X), _ld(X), _p(ptr), _p(perm), _p(out), _ld(out), S, H, int(mean),
-                                  int(accumulate), _p(amax_out), _stream()), "mi_segment_reduce")
+                                  int(accumulate), _p(amax_out), int(rows), _stream()), "mi_segment_reduce")
     return out
 
 
@@ -220,6 +228,18 @@ def layernorm_fwd(x, gamma, beta, y, rows, H, mean=None, rstd=None, eps=1e-5, am
     check(lib().mi_layernorm_fwd(_p(x), _ld(x), _p(gamma), _p(beta), _p(y), _ld(y), _p(mean), _p(rstd), rows, H,
                                  eps, _p(amax_out), _stream()), "mi_layernorm_fwd")
     return y
+
+
+def layernorm_fwd_split(x, gamma, beta, y, y_hi, y_lo, amax, rows, H, zero_out=None, zero_cols=0, mean=None, rstd=None, eps=1e-5):
+    """LayerNorm written as the pre-split fp16 operand pair of tc_gemm_presplit (+ row maxima for its a_amax); y (fp32)
+    optional; zero_out: a companion row block zeroed in the same pass.  See mi_layernorm_fwd_split."""
+    for t in (x, gamma, beta, y, amax, zero_out, mean, rstd):
+        _f32(t)
+    if y_hi.dtype != torch.float16 or y_lo.dtype != torch.float16 or _ld(y_hi) != _ld(y_lo):
+        raise TypeError("y_hi / y_lo must be float16 with equal leading dimensions")
+    check(lib().mi_layernorm_fwd_split(_p(x), _ld(x), _p(gamma), _p(beta), _p(y), _ld(y) if y is not None else 0, _p(y_hi),
+                                       _p(y_lo), _ld(y_hi), _p(amax), _p(zero_out), _ld(zero_out) if zero_out is not None else 0,
+                                       zero_cols, _p(mean), _p(rstd), rows, H, eps, _stream()), "mi_layernorm_fwd_split")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows, H, accumulate_dx=False):
@@ -388,3 +408,30 @@ def composition_reward(Z, node_off, B, tables, mass, modes, targets, minv, maxv,
     check(lib().mi_composition_reward(_p(Z), _p(node_off), B, _p(tables), _p(mass), P, ia(*modes), ia(*targets), da(*minv),
                                       da(*maxv), da(*tval), da(*weight), reduce, _p(props), _p(rewards), _p(failed), _stream()),
           "mi_composition_reward")
+
+
+def node_chain(M, H, agg, amax_agg, wb_hi, wb_lo, bn1, R, an1, amax_an1, w2_hi, w2_lo, bn2, h_in, h, ln=None, zero_out=None):
+    """node_mlp.0 -> node_mlp.2 + residual (h = h_in + ...; h may be h_in) -> [next layer's LayerNorm + P|Q|R GEMM] in one launch.
+    ln = (gamma, beta, eps, wpqr_hi, wpqr_lo, cb [B, 3H], node_graph, pqr [M, 3H]) or None (last layer).  See mi_node_chain."""
+    for t in (agg, amax_agg, bn1, R, an1, amax_an1, bn2, h_in, h, zero_out):
+        _f32(t)
+    if ln is not None:
+        g, b, eps, ph, pl, cb, ng, pqr = ln
+        _f32(g), _f32(b), _f32(cb), _f32(pqr), _i32(ng)
+        tail = (_p(g), _p(b), float(eps), _p(ph), _p(pl), _p(cb), _ld(cb), _p(ng), _p(pqr), _ld(pqr))
+    else:
+        tail = (None, None, 1e-5, None, None, None, 0, None, None, 0)
+    check(lib().mi_node_chain(M, H, 3 if ln is not None else 2, _p(agg), _ld(agg), _p(amax_agg), _p(wb_hi), _p(wb_lo), _ld(wb_hi),
+                              _p(bn1), _p(R), _ld(R), _p(an1), _p(amax_an1), _p(w2_hi), _p(w2_lo), _p(bn2), _p(h_in), _ld(h_in), _p(h), _ld(h),
+                              *tail, _p(zero_out), _ld(zero_out) if zero_out is not None else 0, _stream()), "mi_node_chain")
+
+
+def weighted_field_sum(fields, weights, out):
+    """out[b] = sum_k weights[k] * fields[k][b]  (<= 4 per-sample loss vectors).  See mi_weighted_field_sum."""
+    for t in list(fields) + [out]:
+        _f32(t)
+    F = len(fields)
+    ptrs = [_p(t) for t in fields] + [None] * (4 - F)
+    check(lib().mi_weighted_field_sum(out.numel(), F, *ptrs, (C.c_float * F)(*[float(w) for w in weights]), _p(out), _stream()),
+          "mi_weighted_field_sum")
+    return out

@@ -44,10 +44,12 @@ def cell_length_mask(sample_data, max_len=MAX_CELL_LENGTH, device=None):
     return validity_masks(sample_data, device=device, max_len=max_len)[0]
 
 
-def invalid_filter(sample_data, sample_struc, return_mask=False, structure_validity=True, smact_validity=None, device=None):
+def invalid_filter(sample_data, sample_struc, return_mask=False, structure_validity=True, smact_validity=None, device=None,
+                   **thresholds):
     """opt_filter.py:50-63.  structure_validity: True = the device predicate, a callable = the caller's own (e.g.
-    mattergen's), None/False = skipped; smact_validity: a callable over structures or None (skipped)."""
-    cell_ok, struc_ok, _ = validity_masks(sample_data, device=device)
+    mattergen's), None/False = skipped; smact_validity: a callable over structures or None (skipped); thresholds
+    (max_len, min_dist, min_vol, hard_len) default to the reference's."""
+    cell_ok, struc_ok, _ = validity_masks(sample_data, device=device, **thresholds)
     mask = cell_ok.copy()
     if structure_validity is True:
         mask &= struc_ok

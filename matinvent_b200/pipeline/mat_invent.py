@@ -94,7 +94,9 @@ class MatInvent(ReinL):
         self.timing["sample_s"] = time.time() - t0
         t0 = time.time()
         n_gen = len(data)
-        if hooks["invalid_filter"] is not False:
+        if callable(hooks["invalid_filter"]):             # the caller's own filter in place of the default
+            data, strucs = hooks["invalid_filter"](data, strucs)
+        elif hooks["invalid_filter"] is not False:
             data, strucs = invalid_filter(data, strucs, device=self.device,
                                           structure_validity=hooks["structure_validity"] if hooks["structure_validity"] is not None else True,
                                           smact_validity=hooks["smact_validity"])

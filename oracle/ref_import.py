@@ -13,8 +13,40 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("MATINVENT_REFERENCE", "/root/reference")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# staged copy of the four reference files the sampler needs (git-ignored, shipped to the GPU box by gpurun, written by
+# stage_reference() in the build container): lets bench.py time the UNMODIFIED reference where /root/reference is absent
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+STAGED_FILES = ("cspnet.py", "diffusion.py", "scheduler.py", "utils.py")
+
+
+def _pick_root():
+    env = os.environ.get("MATINVENT_REFERENCE")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "models", "diffcsp", "cspnet.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REF_ROOT = _pick_root()
+
+
+def stage_reference():
+    """copy models/diffcsp/{cspnet,diffusion,scheduler,utils}.py, unmodified, from the reference tree into
+    baseline/_ref/ (build container only; returns the staged root, or None where the reference tree is absent)"""
+    import filecmp
+    import shutil
+    src = os.path.join("/root/reference", "models", "diffcsp")
+    if not os.path.isfile(os.path.join(src, "cspnet.py")):
+        return None
+    dst = os.path.join(STAGED_ROOT, "models", "diffcsp")
+    os.makedirs(dst, exist_ok=True)
+    for f in STAGED_FILES:
+        if not os.path.isfile(os.path.join(dst, f)) or not filecmp.cmp(os.path.join(src, f), os.path.join(dst, f), shallow=False):
+            shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+    return STAGED_ROOT
 
 
 def reference_available():
@@ -134,3 +166,23 @@ def import_reference_reward():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def import_reference_mattergen_adapter():
+    """The reference's in-tree MatterGen adapter, unmodified: (models.mattergen.pl_module, models.mattergen.loss) under the
+    stub `mattergen` leaves of oracle/shims/mattergen."""
+    if not os.path.isfile(os.path.join(REF_ROOT, "models", "mattergen", "pl_module.py")):
+        raise RuntimeError("reference MatterGen adapter not found under %s" % REF_ROOT)
+    for p in (REF_ROOT, _SHIMS):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, _SHIMS)
+    import importlib
+    loss = importlib.import_module("models.mattergen.loss")
+    plm = importlib.import_module("models.mattergen.pl_module")
+    return plm, loss
+
+
+def mattergen_adapter_available():
+    return os.path.isfile(os.path.join(REF_ROOT, "models", "mattergen", "pl_module.py"))

@@ -180,9 +180,18 @@ def test_rl_loop_plumbing(tmp_path):
     np.random.seed(0)
     torch.manual_seed(0)
     suite = _suite(tmp_path)
-    # a random-init net puts atoms anywhere: only the in-tree cell-length rule filters here (structure_validity=False)
+    # a random-init net blows the cells up (|l| ~ 1e2..1e5) and puts atoms anywhere: the device pre-filter runs with
+    # thresholds that let these crystals through (the reference thresholds are tested in test_gpu_postsample.py)
+    import functools
+    from matinvent_b200.pipeline.filters import invalid_filter
+    calls = []
+
+    def loose_filter(data, strucs):
+        calls.append(len(data))
+        return invalid_filter(data, strucs, device="cuda", structure_validity=False, max_len=1e30)
+
     pipe = MatInvent(rl_epoch=2, model_suite=suite, reward=StandInHHIReward(),
-                     sample_cfg=dict(filter=None, max_num=4, structure_validity=False),
+                     sample_cfg=dict(filter=None, max_num=4, invalid_filter=loose_filter),
                      finetune_cfg=dict(batch_size=4, accum_steps=5, epochs=1, sigma=0.025), save_dir=str(tmp_path),
                      save_freq=1, device="cuda", replay=True, replay_args=dict(buffer_size=10, sample_size=2, reward_cutoff=0.0))
     w0 = pipe.agent.decoder.flat.data.clone()
@@ -191,7 +200,7 @@ def test_rl_loop_plumbing(tmp_path):
     assert not torch.equal(pipe.agent.decoder.flat.data, w0) and torch.equal(pipe.prior.decoder.flat.data, p0)
     assert torch.isfinite(pipe.agent.decoder.flat.data).all()
     # max_num caps what is scored (pipeline/mat_invent.py:110-114): 2 iterations x min(8 sampled, 4) crystals
-    assert len(pipe.replay) > 0 and pipe.cost == 8
+    assert len(pipe.replay) > 0 and pipe.cost == 8 and calls == [8, 8]
     assert os.path.isfile(tmp_path / "models" / "final" / "last.ckpt")
     # the reference's per-iteration dumps: valid / eval extxyz and the long-term-memory csv (:82-86, 117-121, 212)
     from matinvent_b200.pipeline.utils import read_extxyz
@@ -205,6 +214,7 @@ def test_rl_step_device_reward_and_filter(tmp_path):
     """one RL iteration with every post-sampling stage on the device: validity pre-filter, multi-objective composition
     reward (min of two scaled properties, BASELINE configs[4] style), diversity filter, replay buffer"""
     from matinvent_b200.pipeline import MatInvent
+    from matinvent_b200.pipeline.filters import invalid_filter
     from matinvent_b200.rewards import CompositionReward, synthetic_table
     np.random.seed(1)
     torch.manual_seed(1)
@@ -213,7 +223,9 @@ def test_rl_step_device_reward_and_filter(tmp_path):
         prop_cfg=[dict(name="hhi", table=synthetic_table("hhi"), target="descending", minv=750, maxv=3250),
                   dict(name="magmom", table=synthetic_table("magmom"), weights="atom", target="ascending", minv=0.0, maxv=0.25)],
         reward_threshold=0.8, reduce="min", device="cuda")
-    pipe = MatInvent(rl_epoch=1, model_suite=suite, reward=reward, sample_cfg=dict(structure_validity=False),
+    pipe = MatInvent(rl_epoch=1, model_suite=suite, reward=reward,
+                     sample_cfg=dict(invalid_filter=lambda d, s: invalid_filter(d, s, device="cuda", structure_validity=False,
+                                                                                max_len=1e30)),
                      finetune_cfg=dict(batch_size=8, accum_steps=5, epochs=1, sigma=0.025), save_dir=str(tmp_path), save_freq=1,
                      device="cuda", replay=True, replay_args=dict(buffer_size=10, sample_size=2, reward_cutoff=0.0),
                      div_filter=True, df_args=dict(tol=3, buff=6))

@@ -229,3 +229,137 @@ def test_tc_gemm_split_k_accumulates_weight_gradient(M, N, K, ks):
     col_err = ((G.double() - G0.double()) - ref).abs().amax(dim=0) / (dY.double().abs().t() @ X.double().abs()).amax(dim=0)
     print("split-K weight gradient M=%d N=%d K=%d ks=%d: %.2e" % (M, N, K, ks, float(col_err.max())))
     assert float(col_err.max()) < 1e-5
+
+
+# ---------------------------------------------------------------- round 2: fused scatter-mean epilogue, LayerNorm -> pre-split operand
+def _segments(sizes, seed=0):
+    """consecutive-row segments: (idx [M] int32, weight [M] = 1 / segment length, ptr)"""
+    idx = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    w = (1.0 / torch.tensor(sizes, dtype=torch.float32))[idx]
+    return idx.int().cuda(), w.cuda()
+
+
+@pytest.mark.parametrize("sizes_kind,train", [("fc", False), ("fc", True), ("ragged", False), ("one", False)])
+def test_tc_gemm_fused_scatter_mean(sizes_kind, train):
+    """mi_tc_gemm with epi->scat_*: silu(A W^T + b) reduced to segment means in the epilogue (cspnet.py:73-79) against
+    float64; segments straddle the 32-row windows and the 128-row tiles, rows past M are ignored, the reported maxima
+    bound the means"""
+    from matinvent_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    if sizes_kind == "fc":          # n^2 edges per crystal in runs of n, like fc edges: 1..20 rows per segment
+        ns = torch.randint(1, 21, (230,), generator=g).tolist()
+        sizes = [n for n in ns for _ in range(n)]
+    elif sizes_kind == "ragged":
+        sizes = torch.randint(1, 60, (400,), generator=g).tolist()       # longer than a 32-row window too
+    else:
+        sizes = [1] * 517
+    M, N, K = sum(sizes), 512, 512
+    A = _rand(M, K, seed=4) * torch.exp(2 * _rand(M, 1, seed=5))
+    W, bias = _rand(N, K, seed=6) / K ** 0.5, _rand(N, seed=7)
+    mhi, mlo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=torch.float16)
+    inv = torch.empty(N, device="cuda")
+    ops.f16_split_rows(W, mhi, mlo, inv)
+    idx, w = _segments(sizes)
+    S = len(sizes)
+    out = torch.zeros(S, 2 * N, device="cuda")
+    agg = out[:, N:]                                   # strided destination (cat[:, H:])
+    amax = torch.zeros(S, device="cuda")
+    Z = torch.empty(M, N, device="cuda") if train else None
+    ops.tc_gemm(A, mhi, mlo, None, M=M, bias=bias, z_out=Z, act=ops.ACT_SILU, a_amax=A.abs().amax(1).contiguous(), col_scale=inv,
+                flags=ops.TC_MERGED, scatter=(agg, idx, w, amax))
+    z = A.double() @ W.double().t() + bias.double()
+    y = torch.nn.functional.silu(z)
+    ref = torch.zeros(S, N, dtype=torch.float64, device="cuda").index_add_(0, idx.long(), y)
+    ref /= torch.tensor(sizes, dtype=torch.float64, device="cuda")[:, None]
+    assert rel_err(agg, ref) < 6e-6, rel_err(agg, ref)
+    assert float(out[:, :N].abs().max()) == 0.0                             # nothing written outside the destination
+    if train:
+        assert rel_err(Z, z) < 5e-6
+    rowmax = ref.abs().amax(1).float()
+    ymax = torch.zeros(S, dtype=torch.float64, device="cuda").index_reduce_(0, idx.long(), y.abs().amax(1), "amax").float()
+    assert bool((amax >= rowmax * (1 - 1e-5)).all()) and bool((amax <= ymax * (1 + 1e-5)).all())
+    # run to run bit-identical for fc-sized segments (at most two partial sums per destination element)
+    if sizes_kind == "fc":
+        out2 = torch.zeros(S, 2 * N, device="cuda")
+        ops.tc_gemm(A, mhi, mlo, None, M=M, bias=bias, act=ops.ACT_SILU, a_amax=A.abs().amax(1).contiguous(), col_scale=inv,
+                    flags=ops.TC_MERGED, scatter=(out2[:, N:], idx, w, None))
+        assert torch.equal(out2[:, N:], agg)
+
+
+def test_layernorm_split_feeds_presplit_gemm():
+    """mi_layernorm_fwd_split: LayerNorm (cspnet.py:86-88) written as the pre-split fp16 operand of mi_tc_gemm_presplit
+    with the row scale its a_amax implies; the GEMM on it against float64 LayerNorm @ W^T; rows spanning 1e-4..1e6"""
+    from matinvent_b200 import ops
+    rows, H, N = 777, 512, 1536
+    x = _rand(rows, H, seed=1) * torch.exp(4 * _rand(rows, 1, seed=2)) * (1 + 0.3 * _rand(rows, 1, seed=3))
+    gamma, beta = 1 + 0.3 * _rand(H, seed=4), 0.2 * _rand(H, seed=5)
+    gamma[7] = 300.0                                   # one large affine weight: row maxima far above sqrt(H)
+    W = _rand(N, H, seed=6) / H ** 0.5
+    hi, lo = _split(ops, W)
+    y = torch.empty(rows, 2 * H, device="cuda")
+    yh, yl = torch.empty(rows, H, device="cuda", dtype=torch.float16), torch.empty(rows, H, device="cuda", dtype=torch.float16)
+    amax = torch.empty(rows, device="cuda")
+    tail = torch.full((rows, 2 * H), 7.0, device="cuda")
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd_split(x, gamma, beta, y[:, :H], yh, yl, amax, rows, H, zero_out=tail[:, H:], zero_cols=H, mean=mean, rstd=rstd)
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), gamma.double(), beta.double(), 1e-5)
+    assert float(((y[:, :H].double() - ref).abs().amax(1) / ref.abs().amax(1)).max()) < 3e-6
+    y2 = torch.empty(rows, H, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, y2, rows, H)
+    assert torch.equal(y2, y[:, :H])                                        # same arithmetic as the plain kernel
+    assert torch.equal(amax, y2.abs().amax(1))
+    assert float(tail[:, H:].abs().max()) == 0.0 and float(tail[:, :H].min()) == 7.0
+    assert float(((mean.double() - x.double().mean(1)).abs() / x.double().abs().amax(1)).max()) < 1e-6
+    # the operand pair reproduces the row to 2^-22 of its maximum once the row scale is undone
+    e = torch.floor(torch.log2(amax)) - 14
+    rec = (yh.double() + yl.double() / 2048) * torch.exp2(e.double())[:, None]
+    assert float(((rec - y2.double()).abs() / amax.double()[:, None]).max()) < 2.0 ** -21
+    Cb = _rand(9, N, seed=8)
+    ib = torch.randint(0, 9, (rows,), generator=torch.Generator().manual_seed(9)).int().cuda()
+    C = torch.empty(rows, N, device="cuda")
+    ops.tc_gemm_presplit(yh, yl, hi, lo, C, M=rows, gathers=[(Cb, ib)], a_amax=amax)
+    want = ref @ W.double().t() + Cb.double()[ib.long()]
+    err = float(((C.double() - want).abs().amax(1) / want.abs().amax(1)).max())
+    print("LN -> presplit GEMM: worst row error %.2e" % err)
+    assert err < 6e-6, err
+
+
+@pytest.mark.parametrize("num_atoms", [[4, 11, 20, 8], [20] * 13 + [1, 1, 3], "bench"])
+def test_node_chain_matches_separate_kernels(gold_full, num_atoms):
+    """mi_node_chain (one cluster launch per layer boundary: node_mlp.0 -> node_mlp.2 + residual -> next LayerNorm -> next
+    P|Q|R GEMM) against the same forward through the separate kernels, and both against the oracle: row counts below,
+    across and far above the 128-row blocks"""
+    import numpy as np
+    from oracle import diffcsp_oracle as O
+    from test_gpu_parity import _full_module
+    from matinvent_b200.models.diffcsp.sample import ATOM_DIST
+    if num_atoms == "bench":
+        num_atoms = np.random.RandomState(0).choice(21, 256, p=ATOM_DIST["mp_20"]).tolist()
+    na = torch.tensor(num_atoms)
+    B, N = len(na), int(na.sum())
+    g = torch.Generator().manual_seed(3)
+    t = torch.randn(B, 256, generator=g)
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = torch.randn(B, 3, 3, generator=g) + 4.0 * torch.eye(3)
+    n2g = torch.repeat_interleave(torch.arange(B), na)
+    m = _full_module(gold_full)
+    outs = []
+    for chain in (True, False):
+        m.decoder.use_chain = chain
+        with torch.no_grad():
+            outs.append([o.clone() for o in m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)])
+    for u, v in zip(*outs):
+        assert rel_err(u, v) < 3e-6, rel_err(u, v)
+    sd = O.init_params(gold_full["hp"], gold_full["seeds"][0])
+    with torch.no_grad():
+        ref = O.cspnet_forward(sd, gold_full["hp"], t, a, x, l, na, n2g)
+    errs = [rel_err(u, r) for u, r in zip(outs[0], ref)]
+    print("node chain forward vs oracle (%d rows): %s" % (N, " ".join("%.2e" % e for e in errs)))
+    assert max(errs) < 2e-5, errs
+    # a second call on the same workspace gives the same bits (every buffer the chain reuses is re-initialised)
+    m.decoder.use_chain = True
+    with torch.no_grad():
+        again = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+    for u, v in zip(outs[0], again):
+        assert torch.equal(u, v)

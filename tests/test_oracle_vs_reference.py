@@ -155,3 +155,68 @@ def test_reward_scoring_oracle_matches_live_reference(tmp_path):
             assert np.array_equal(r1, r2) and np.array_equal(f1, f2), (reduce, sel)
             for k in d1:
                 assert np.array_equal(d1[k], d2[k]), k
+
+
+# ---------------------------------------------------------------- MatterGen adapter (in-tree arithmetic only)
+class _FakeBatch:
+    """duck-typed ChemGraph batch: fields by key, batch indices per field, batch size"""
+
+    def __init__(self, fields, batch_idx, B):
+        self.fields, self._bi, self.B = fields, batch_idx, B
+
+    def __getitem__(self, k):
+        return self.fields[k]
+
+    def __contains__(self, k):
+        return k in self.fields
+
+    def get_batch_idx(self, k):
+        return None if k == "cell" else self._bi
+
+    def get_batch_size(self):
+        return self.B
+
+
+@pytest.mark.skipif(not R.mattergen_adapter_available(), reason="reference MatterGen adapter not present")
+def test_mattergen_adapter_oracle_matches_live_reference():
+    """oracle/mattergen_oracle.py against the UNMODIFIED models/mattergen/{pl_module,loss}.py (stub mattergen leaves):
+    the fine-tune time of every index, the per-sample weighted loss aggregation, the KL proxy — bit for bit"""
+    import types
+    from oracle import mattergen_oracle as MO
+    plm, loss_mod = R.import_reference_mattergen_adapter()
+    g = torch.Generator().manual_seed(0)
+    B, na = 5, torch.tensor([3, 1, 7, 20, 4])
+    N = int(na.sum())
+    bi = torch.repeat_interleave(torch.arange(B), na)
+    seen = {}
+
+    class Corr:
+        T = 1.0
+        corruptions = {"pos": "cp", "cell": "cc", "atomic_numbers": "ca"}
+
+        def sample_marginal(self, batch, t):
+            seen["t"] = t.clone()
+            return "noisy"
+
+    dm = types.SimpleNamespace(pre_corruption_fn=lambda b: b, corruption=Corr(), _get_device=lambda b: torch.device("cpu"),
+                               model=None, loss_fn=None)
+    ref = plm.MatterGenModule(diffusion_module=dm)
+    batch = _FakeBatch({}, bi, B)
+    for ts in (0, 1, 17, 499, 500, 998, 999):
+        noisy, b2, t = ref.add_noise(batch, ts)
+        assert noisy == "noisy" and b2 is batch and t.shape == (B,)
+        assert torch.equal(t, torch.full((B,), float(MO.finetune_time(1.0, ts)))), ts
+    # per-sample aggregation with stub per-field losses (what MaterialsLoss would compute is un-vendored)
+    vals = {"pos": torch.rand(B, generator=g), "cell": torch.rand(B, generator=g), "atomic_numbers": torch.rand(B, generator=g)}
+    sl = loss_mod.SampleLoss()
+    sl.loss_fns = {k: (lambda k_: (lambda **kw: vals[k_]))(k) for k in sl.loss_fns}
+    fb = _FakeBatch({k: None for k in vals}, bi, B)
+    agg, metrics = sl(multi_corruption=Corr(), batch=fb, noisy_batch=fb, score_model_output=fb, t=torch.zeros(B))
+    agg2, metrics2 = MO.aggregate_sample_loss({k: vals[k] for k in sl.loss_fns}, sl.loss_weights)
+    assert torch.equal(agg, agg2) and sl.loss_weights == MO.DEFAULT_WEIGHTS
+    assert all(torch.equal(metrics[k], metrics2[k]) for k in metrics)
+    # KL proxy
+    ap = {"pos": torch.randn(N, 3, generator=g), "cell": torch.randn(B, 3, 3, generator=g), "atomic_numbers": torch.randn(N, 101, generator=g)}
+    pp = {k: v + 0.1 * torch.randn(v.shape, generator=g) for k, v in ap.items()}
+    kl = ref.calc_kl_reg(ap, pp, batch)
+    assert torch.equal(kl, MO.kl_reg(ap, pp, bi, B))
