@@ -183,7 +183,7 @@ class CSPNet(nn.Module):
         # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
-        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
+        self.use_chain = os.environ.get("MI_NODE_CHAIN", "0") != "0"      # fused node-level chain (inference, H = 512): measured slower than the separate launches (profiles/r2a_breakdown_*.txt)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
         # transposed copies W^T (fp16 head / tail) of the weights whose input gradients run on the tensor cores
