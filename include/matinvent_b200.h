@@ -117,21 +117,26 @@ int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo,
                         mi_stream_t stream);
 
 /* The node-level chain of a CSPNet layer boundary in ONE launch (inference; hidden_dim H = 512): thread-block clusters of
- * four CTAs own 128 rows each, phases separated by cluster barriers, intermediates through L2 (csrc/mi_node.cu):
- *   phase 0  an1 = silu(agg W_b^T + R + bn1)        node_mlp.0 (cspnet.py:77-82); W_b = node_mlp.0.weight[:, H:] as fp16
+ * four CTAs own 128 rows each, phases separated by cluster barriers, every intermediate operand written pre-split (fp16
+ * hi / 2^11-scaled lo, [M, H], row stride H) by the producing epilogue (csrc/mi_node.cu):
+ *   prologue xs = split(agg) with the row scales amax_agg calls for; zero_agg != 0: agg is zeroed afterwards (the next fused
+ *            scatter-mean's destination)
+ *   phase 0  ys = split(silu(agg W_b^T + R + bn1))      node_mlp.0 (cspnet.py:77-82); W_b = node_mlp.0.weight[:, H:] as fp16
  *                                                   (hi, lo) with row stride ld_wb, R = LN(h) node_mlp.0.weight[:, :H]^T
- *                                                   (third block of the previous [P'|Q|R] GEMM), amax_agg = row maxima of agg
- *   phase 1  h   = h_in + silu(an1 W_2^T + bn2)     node_mlp.2 + residual (cspnet.py:82, 91); h may alias h_in
- *   phase 2  pqr = LN(h; ln_g, ln_b) W_pqr^T + cb[node_graph]   the NEXT layer's LayerNorm and per-node GEMM, W_pqr [3H, H];
- *            zero_out (nullable): H floats per row are zeroed (the next fused scatter-mean's destination; may alias agg)
- * n_phases = 2 stops after phase 1 (last layer).  amax_an1 [M] must be zeroed by the caller.  Replaces four launches
- * (mi_tc_gemm x3 + mi_layernorm_fwd_split) with the same arithmetic. */
-int mi_node_chain(int M, int H, int n_phases, const float* agg, int ld_agg, const float* amax_agg, const void* wb_hi,
-                  const void* wb_lo, int ld_wb, const float* bn1, const float* R, int ld_r, float* an1, float* amax_an1,
-                  const void* w2_hi, const void* w2_lo, const float* bn2, const float* h_in, int ld_hin, float* h, int ld_h,
-                  const float* ln_g,
-                  const float* ln_b, float ln_eps, const void* wpqr_hi, const void* wpqr_lo, const float* cb, int ld_cb,
-                  const int* node_graph, float* pqr, int ld_pqr, float* zero_out, int ld_zero, mi_stream_t stream);
+ *                                                   (third block of the previous [P'|Q|R] GEMM, whose row maxima are amax_pqr)
+ *   phase 1  h   = h_in + silu(an1 W_2^T + bn2)     node_mlp.2 + residual (cspnet.py:82, 91); h may alias h_in;
+ *            xs  = split(LN(h; ln_g, ln_b))          the NEXT layer's LayerNorm (cspnet.py:86-88)
+ *   phase 2  pqr = LN(h) W_pqr^T + cb[node_graph]   its per-node GEMM, W_pqr [3H, H]; amax_next [M] (zeroed by the caller)
+ *            receives the row maxima of pqr
+ * n_phases = 2 stops after phase 1's residual (last layer).  bounds: 3 device floats {max_j ||W_b[j]||_1, max |bn1|,
+ * sqrt(H) max |ln_g| + max |ln_b|} (each rounded UP): the row scales of ys and of the LN operand come from these a-priori
+ * bounds of the row maxima, not from the maxima.  Replaces four launches (mi_tc_gemm x3 + mi_layernorm_fwd_split). */
+int mi_node_chain(int M, int H, int n_phases, float* agg, int ld_agg, const float* amax_agg, int zero_agg, void* xs_hi,
+                  void* xs_lo, void* ys_hi, void* ys_lo, const void* wb_hi, const void* wb_lo, int ld_wb, const float* bn1,
+                  const float* R, int ld_r, const float* amax_pqr, const float* bounds, const void* w2_hi, const void* w2_lo,
+                  const float* bn2, const float* h_in, int ld_hin, float* h, int ld_h, const float* ln_g, const float* ln_b,
+                  float ln_eps, const void* wpqr_hi, const void* wpqr_lo, const float* cb, int ld_cb, const int* node_graph,
+                  float* pqr, int ld_pqr, float* amax_next, mi_stream_t stream);
 
 /* Transposes that put the weight-gradient GEMM dW[N_out, K_in] += dY^T X (a sum over tens of thousands of edge or node
  * rows) into the K-contiguous form of mi_tc_gemm: dY^T is its fp32 A operand (row maxima = column maxima of dY), X^T

@@ -65,6 +65,9 @@ class _Workspace:
         self.pq = self.pqr[:, :2 * H]
         self.hn_hi = torch.empty(N, H, device=dev, dtype=torch.float16)      # LN(h) as a pre-split tensor-core operand
         self.hn_lo = torch.empty(N, H, device=dev, dtype=torch.float16)
+        # operand pairs written by the node chain's epilogues (mi_node_chain): xs = split(agg) / split(LN(h)), ys = split(an1)
+        self.xs = (torch.empty(N, H, device=dev, dtype=torch.float16), torch.empty(N, H, device=dev, dtype=torch.float16))
+        self.ys = (torch.empty(N, H, device=dev, dtype=torch.float16), torch.empty(N, H, device=dev, dtype=torch.float16))
         self.a1 = [buf(E, H) for _ in range(nl)]
         self.a2 = buf(E, H)
         self.an1 = [buf(N, H) for _ in range(nl)]
@@ -76,15 +79,16 @@ class _Workspace:
         self.pred_a = buf(N, A)
         # row-wise max |.| of the activations that feed tensor-core GEMMs (power-of-two row rescaling keeps the
         # fp16 split path inside fp32 dynamic range); zeroed at the start of every forward
-        self.amax = torch.zeros(N + L * (E + 3 * N), device=dev, dtype=f32)
+        self.amax = torch.zeros(N + L * (E + 4 * N), device=dev, dtype=f32)
         self.amax_h0 = self.amax[:N]
         o = N
-        self.amax_a1, self.amax_agg, self.amax_an1, self.amax_hn = [], [], [], []
+        self.amax_a1, self.amax_agg, self.amax_an1, self.amax_hn, self.amax_pqr = [], [], [], [], []
         for _ in range(L):
             self.amax_a1.append(self.amax[o:o + E]); o += E
             self.amax_agg.append(self.amax[o:o + N]); o += N
             self.amax_an1.append(self.amax[o:o + N]); o += N
             self.amax_hn.append(self.amax[o:o + N]); o += N
+            self.amax_pqr.append(self.amax[o:o + N]); o += N      # row maxima of [P'|Q|R]: the bounds of the node chain
         if train:
             self.z1 = [buf(E, H) for _ in range(L)]
             self.z2 = [buf(E, H) for _ in range(L)]
@@ -183,9 +187,10 @@ class CSPNet(nn.Module):
         # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
-        self.use_chain = os.environ.get("MI_NODE_CHAIN", "0") != "0"      # fused node-level chain (inference, H = 512): measured slower than the separate launches (profiles/r2a_breakdown_*.txt)
+        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
+        self._bounds = None
         # transposed copies W^T (fp16 head / tail) of the weights whose input gradients run on the tensor cores
         # (dX = dY W is the forward kernel with W^T as its weight); built once a backward has asked for them
         self._hiT, self._loT, self._wT = {}, {}, {}
@@ -210,6 +215,7 @@ class CSPNet(nn.Module):
         self._flat_hi = self._flat_lo = None
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
+        self._bounds = None
         self._hiT, self._loT, self._wT = {}, {}, {}
         self._tc_version = None
         return r
@@ -251,6 +257,17 @@ class CSPNet(nn.Module):
             for dst, src in ((self._pqr_hi[i], self._hi), (self._pqr_lo[i], self._lo)):
                 dst[:2 * H].copy_(src[q + "w_pq"])
                 dst[2 * H:].copy_(src[q + "wn1"][:, :H])
+        # a-priori bounds of the node chain's row scales (mi_node_chain), rounded up: {max_j ||W_b[j]||_1, max |b_n1|,
+        # sqrt(H) max |gamma| + max |beta| of the NEXT layer's LayerNorm}
+        if self._bounds is None:
+            self._bounds = torch.zeros(self.num_layers, 4, device=self.flat.device, dtype=torch.float32)
+        for i in range(self.num_layers):
+            q = "l%d." % i
+            self._bounds[i, 0] = self._views[q + "wn1"][:, H:].abs().sum(1).max() * 1.001
+            self._bounds[i, 1] = self._views[q + "bn1"].abs().max() * 1.001
+            if i + 1 < self.num_layers:
+                qn = "l%d." % (i + 1)
+                self._bounds[i, 2] = (math.sqrt(H) * self._views[qn + "ln_g"].abs().max() + self._views[qn + "ln_b"].abs().max()) * 1.001
         if self._need_T:
             for i in range(self.num_layers):
                 for k in ("l%d.wn2" % i, "l%d.wn1" % i, "l%d.w2" % i, "l%d.w_pq" % i):
@@ -541,17 +558,17 @@ class CSPNet(nn.Module):
                     ops.layernorm_fwd_split(h_in, W[q + "ln_g"], W[q + "ln_b"], None, ws.hn_hi, ws.hn_lo, ws.amax_hn[i], N, H,
                                             zero_out=agg if merged else None, zero_cols=H)
                     ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr, M=N,
-                                         gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i])
+                                         gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i], amax_out=ws.amax_pqr[i])
                 self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
                 self.edge_gemm2(i, ws, g, E, a1, agg, train, merged)
                 nxt = None
                 if i + 1 < L:
                     qn = "l%d." % (i + 1)
                     nxt = (W[qn + "ln_g"], W[qn + "ln_b"], 1e-5, self._pqr_hi[i + 1], self._pqr_lo[i + 1], ws.cb[i + 1],
-                           g.node_graph, ws.pqr)
-                ops.node_chain(N, H, agg, ws.amax_agg[i], self._hi[q + "wn1"][:, H:], self._lo[q + "wn1"][:, H:], W[q + "bn1"],
-                               ws.pqr[:, 2 * H:], an1, ws.amax_an1[i], self._hi[q + "wn2"], self._lo[q + "wn2"], W[q + "bn2"],
-                               h_in, h_out, ln=nxt, zero_out=agg)
+                           g.node_graph, ws.pqr, ws.amax_pqr[i + 1])
+                ops.node_chain(N, H, agg, ws.amax_agg[i], merged and i + 1 < L, ws.xs, ws.ys, self._hi[q + "wn1"][:, H:],
+                               self._lo[q + "wn1"][:, H:], W[q + "bn1"], ws.pqr[:, 2 * H:], ws.amax_pqr[i], self._bounds[i],
+                               self._hi[q + "wn2"], self._lo[q + "wn2"], W[q + "bn2"], h_in, h_out, ln=nxt)
                 continue
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts; the
             # per-crystal term C_b is folded into P (P'_i = P_i + C_b(i)) by the per-node GEMM's epilogue: the per-edge

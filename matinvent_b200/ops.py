@@ -410,20 +410,25 @@ def composition_reward(Z, node_off, B, tables, mass, modes, targets, minv, maxv,
           "mi_composition_reward")
 
 
-def node_chain(M, H, agg, amax_agg, wb_hi, wb_lo, bn1, R, an1, amax_an1, w2_hi, w2_lo, bn2, h_in, h, ln=None, zero_out=None):
+def node_chain(M, H, agg, amax_agg, zero_agg, xs, ys, wb_hi, wb_lo, bn1, R, amax_pqr, bounds, w2_hi, w2_lo, bn2, h_in, h, ln=None):
     """node_mlp.0 -> node_mlp.2 + residual (h = h_in + ...; h may be h_in) -> [next layer's LayerNorm + P|Q|R GEMM] in one launch.
-    ln = (gamma, beta, eps, wpqr_hi, wpqr_lo, cb [B, 3H], node_graph, pqr [M, 3H]) or None (last layer).  See mi_node_chain."""
-    for t in (agg, amax_agg, bn1, R, an1, amax_an1, bn2, h_in, h, zero_out):
+    xs, ys = (hi, lo) fp16 [M, H] scratch operand pairs; bounds = 3 device floats (see mi_node_chain);
+    ln = (gamma, beta, eps, wpqr_hi, wpqr_lo, cb [B, 3H], node_graph, pqr [M, 3H], amax_next [M]) or None (last layer)."""
+    for t in (agg, amax_agg, bn1, R, amax_pqr, bounds, bn2, h_in, h):
         _f32(t)
+    for t in (*xs, *ys):
+        if t.dtype != torch.float16 or not t.is_contiguous() or t.shape[1] != H:
+            raise TypeError("xs / ys must be contiguous fp16 [M, H]")
     if ln is not None:
-        g, b, eps, ph, pl, cb, ng, pqr = ln
-        _f32(g), _f32(b), _f32(cb), _f32(pqr), _i32(ng)
-        tail = (_p(g), _p(b), float(eps), _p(ph), _p(pl), _p(cb), _ld(cb), _p(ng), _p(pqr), _ld(pqr))
+        g, b, eps, ph, pl, cb, ng, pqr, amax_next = ln
+        _f32(g), _f32(b), _f32(cb), _f32(pqr), _i32(ng), _f32(amax_next)
+        tail = (_p(g), _p(b), float(eps), _p(ph), _p(pl), _p(cb), _ld(cb), _p(ng), _p(pqr), _ld(pqr), _p(amax_next))
     else:
-        tail = (None, None, 1e-5, None, None, None, 0, None, None, 0)
-    check(lib().mi_node_chain(M, H, 3 if ln is not None else 2, _p(agg), _ld(agg), _p(amax_agg), _p(wb_hi), _p(wb_lo), _ld(wb_hi),
-                              _p(bn1), _p(R), _ld(R), _p(an1), _p(amax_an1), _p(w2_hi), _p(w2_lo), _p(bn2), _p(h_in), _ld(h_in), _p(h), _ld(h),
-                              *tail, _p(zero_out), _ld(zero_out) if zero_out is not None else 0, _stream()), "mi_node_chain")
+        tail = (None, None, 1e-5, None, None, None, 0, None, None, 0, None)
+    check(lib().mi_node_chain(M, H, 3 if ln is not None else 2, _p(agg), _ld(agg), _p(amax_agg), int(bool(zero_agg)),
+                              _p(xs[0]), _p(xs[1]), _p(ys[0]), _p(ys[1]), _p(wb_hi), _p(wb_lo), _ld(wb_hi), _p(bn1), _p(R), _ld(R),
+                              _p(amax_pqr), _p(bounds), _p(w2_hi), _p(w2_lo), _p(bn2), _p(h_in), _ld(h_in), _p(h), _ld(h),
+                              *tail, _stream()), "mi_node_chain")
 
 
 def weighted_field_sum(fields, weights, out):
