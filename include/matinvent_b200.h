@@ -138,6 +138,25 @@ int mi_node_chain(int M, int H, int n_phases, float* agg, int ld_agg, const floa
                   float ln_eps, const void* wpqr_hi, const void* wpqr_lo, const float* cb, int ld_cb, const int* node_graph,
                   float* pqr, int ld_pqr, float* amax_next, mi_stream_t stream);
 
+/* The two per-edge blocks of a CSPNet layer on CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, both operands
+ * pre-split and staged by TMA; csrc/mi_edge.cu), merged operand format (MI_TC_MERGED).  Inference path of
+ * models/diffcsp/cspnet.py:59-79; N % 256 == 0.
+ *   mi_edge_block1:  a = silu(alpha * (phi W^T) * col_scale[n] + P[src[e]][n] + Q[dst[e]][n]), written as the fp16 pair
+ *       a_hi = fp16(s_e a), a_lo = fp16(s_e a - a_hi) [E, ld_a] with s_e the power of two that brings
+ *       a_bound[e] = wf_bound[0] + amax_pq[src[e]] + amax_pq[dst[e]] into [2^14, 2^15); a_bound [E] is written too (the
+ *       consumer's epi->a_amax).  phi_hi / phi_lo: mi_edge_fourier's merged-format pair (scaled 2^14: alpha = 2^-14);
+ *       w_hi / w_lo / col_scale: mi_f16_split_rows of W [N, K]; amax_pq [nodes]: upper bounds of max |P[i][:]|, |Q[i][:]|;
+ *       wf_bound: one device float >= max |phi W^T| (sqrt(K / 2) max_j ||W[j]||_2 for the Fourier basis).
+ *   mi_edge_block2:  scat_out[scat_idx[e]][n] += scat_w[e] * silu((a W^T)[e][n] * col_scale[n] + bias[n]) with a given as
+ *       block 1 wrote it; scat_out (zeroed by the caller), scat_idx, scat_w, scat_amax as in mi_epilogue_t. */
+int mi_edge_block1(int E, int N, int K, const void* phi_hi, const void* phi_lo, int ld_phi, const void* w_hi, const void* w_lo,
+                   int ld_w, const float* col_scale, float alpha, const float* P, const float* Q, int ld_pq, const int* src,
+                   const int* dst, const float* amax_pq, const float* wf_bound, void* a_hi, void* a_lo, int ld_a,
+                   float* a_bound, mi_stream_t stream);
+int mi_edge_block2(int E, int N, int K, const void* a_hi, const void* a_lo, int ld_a, const float* a_bound, const void* w_hi,
+                   const void* w_lo, int ld_w, const float* col_scale, const float* bias, float* scat_out, int scat_ld,
+                   const int* scat_idx, const float* scat_w, float* scat_amax, mi_stream_t stream);
+
 /* Transposes that put the weight-gradient GEMM dW[N_out, K_in] += dY^T X (a sum over tens of thousands of edge or node
  * rows) into the K-contiguous form of mi_tc_gemm: dY^T is its fp32 A operand (row maxima = column maxima of dY), X^T
  * its pre-split merged-format W operand with one power-of-two scale per row (= per column of X).

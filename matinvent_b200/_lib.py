@@ -38,6 +38,8 @@ PROTOTYPES = {
     "mi_tc_gemm": [i, i, i, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_tc_gemm_presplit": [i, i, i, p, p, i, p, p, i, p, i, C.POINTER(Epilogue), i, p],
     "mi_node_chain": [i, i, i, p, i, p, i, p, p, p, p, p, p, i, p, p, i, p, p, p, p, p, p, i, p, i, p, p, f, p, p, p, i, p, p, i, p, p],
+    "mi_edge_block1": [i, i, i, p, p, i, p, p, i, p, f, p, p, i, p, p, p, p, p, p, i, p, p],
+    "mi_edge_block2": [i, i, i, p, p, i, p, p, p, i, p, p, p, i, p, p, p, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, f, f, p],
     "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, i, p],

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmatinvent_b200.so")
-SOURCES = ["mi_gemm.cu", "mi_ops.cu", "mi_graph.cu", "mi_tc.cu", "mi_node.cu", "mi_pipeline.cu"]
+SOURCES = ["mi_gemm.cu", "mi_ops.cu", "mi_graph.cu", "mi_tc.cu", "mi_node.cu", "mi_edge.cu", "mi_pipeline.cu"]
 HEADERS = ["mi_common.cuh", "mi_tc_common.cuh", os.path.join("..", "..", "include", "matinvent_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]

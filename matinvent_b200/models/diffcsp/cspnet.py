@@ -187,6 +187,8 @@ class CSPNet(nn.Module):
         # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
+        # per-edge blocks on CTA pairs (csrc/mi_edge.cu): inference, merged tiles, LayerNorm'd node path
+        self.use_pair = os.environ.get("MI_EDGE_PAIR", "1") != "0"
         self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
@@ -265,6 +267,8 @@ class CSPNet(nn.Module):
             q = "l%d." % i
             self._bounds[i, 0] = self._views[q + "wn1"][:, H:].abs().sum(1).max() * 1.001
             self._bounds[i, 1] = self._views[q + "bn1"].abs().max() * 1.001
+            # max |Phi W_F^T| <= sqrt(3F) max_j ||W_F[j]||_2: every sin / cos pair of the Fourier basis has unit norm
+            self._bounds[i, 3] = math.sqrt(3 * self.num_freqs) * self._views[q + "w_f"].norm(dim=1).max() * 1.001
             if i + 1 < self.num_layers:
                 qn = "l%d." % (i + 1)
                 self._bounds[i, 2] = (math.sqrt(H) * self._views[qn + "ln_g"].abs().max() + self._views[qn + "ln_b"].abs().max()) * 1.001
@@ -480,9 +484,20 @@ class CSPNet(nn.Module):
         merged = presplit and self.use_merged and H % 256 == 0 and fill
         return presplit, merged
 
+    def pair_mode(self, train, merged):
+        """the CTA-pair kernels of csrc/mi_edge.cu serve the inference path with merged tiles; they take the row maxima of
+        [P'|Q|R] the LayerNorm'd node path reports (ws.amax_pqr)"""
+        return merged and not train and self.use_pair and self.use_tc and self.ln and self.hidden_dim % 256 == 0
+
     def edge_gemm1(self, i, ws, g, E, a1, train, presplit, merged):
         """a1 = silu(Phi W_F^T + P'[src] + Q[dst])   (first edge linear, cspnet.py:59-72, per-edge part)"""
         H, q = self.hidden_dim, "l%d." % i
+        if self.pair_mode(train, merged):
+            a1h, a1l = a1.view(torch.float16).view(2, -1, H)[:, :a1.shape[0]]
+            ops.edge_block1(E, ws.phi_hi, ws.phi_lo, self._mhi[q + "w_f"], self._mlo[q + "w_f"], self._minv[q + "w_f"], 2.0 ** -14,
+                            ws.pq[:, :H], ws.pq[:, H:], g.edge_src, g.edge_dst, ws.amax_pqr[i], self._bounds[i, 3:4], a1h, a1l,
+                            ws.amax_a1[i])
+            return
         epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
                     z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
         if merged:
@@ -498,6 +513,11 @@ class CSPNet(nn.Module):
         Merged tiles: the segment means are formed in the GEMM's epilogue (`agg` must be zeroed: the LayerNorm of the
         layer does it) and the [E, H] messages are never written; otherwise GEMM -> a2 -> segment_reduce."""
         N, H, q = g.N, self.hidden_dim, "l%d." % i
+        if self.pair_mode(train, merged):
+            a1h, a1l = a1.view(torch.float16).view(2, -1, H)[:, :a1.shape[0]]
+            ops.edge_block2(E, a1h, a1l, ws.amax_a1[i], self._mhi[q + "w2"], self._mlo[q + "w2"], self._minv[q + "w2"],
+                            self._views[q + "b2"], agg, g.edge_src, g.edge_w, ws.amax_agg[i])
+            return
         epi2 = dict(bias=self._views[q + "b2"], z_out=ws.z2[i] if train else None, act=ACT_SILU, a_amax=ws.amax_a1[i])
         if merged:
             ops.tc_gemm(a1, self._mhi[q + "w2"], self._mlo[q + "w2"], None, M=E, col_scale=self._minv[q + "w2"],
@@ -578,7 +598,7 @@ class CSPNet(nn.Module):
                                         ws.amax_hn[i], N, H, zero_out=agg if merged else None, zero_cols=H,
                                         mean=ws.ln_mean[i] if train else None, rstd=ws.ln_rstd[i] if train else None)
                 ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr, M=N,
-                                     gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i])
+                                     gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i], amax_out=ws.amax_pqr[i])
             else:
                 if self.ln:
                     # the row maximum of cat = [LN(h) | agg] is accumulated by both producers (LayerNorm here, the scatter below)

@@ -431,6 +431,24 @@ def node_chain(M, H, agg, amax_agg, zero_agg, xs, ys, wb_hi, wb_lo, bn1, R, amax
                               *tail, _stream()), "mi_node_chain")
 
 
+def edge_block1(E, phi_hi, phi_lo, w_hi, w_lo, col_scale, alpha, P, Q, src, dst, amax_pq, wf_bound, a_hi, a_lo, a_bound):
+    """first per-edge block on CTA pairs: (a_hi, a_lo) = split(silu(alpha phi W^T col_scale + P[src] + Q[dst])).  See mi_edge_block1."""
+    _f32(col_scale), _f32(P), _f32(Q), _f32(amax_pq), _f32(wf_bound), _f32(a_bound), _i32(src), _i32(dst)
+    N, K = w_hi.shape
+    check(lib().mi_edge_block1(E, N, K, _p(phi_hi), _p(phi_lo), _ld(phi_hi), _p(w_hi), _p(w_lo), _ld(w_hi), _p(col_scale),
+                               float(alpha), _p(P), _p(Q), _ld(P), _p(src), _p(dst), _p(amax_pq), _p(wf_bound), _p(a_hi), _p(a_lo),
+                               _ld(a_hi), _p(a_bound), _stream()), "mi_edge_block1")
+
+
+def edge_block2(E, a_hi, a_lo, a_bound, w_hi, w_lo, col_scale, bias, scat_out, scat_idx, scat_w, scat_amax):
+    """second per-edge block + scatter-mean on CTA pairs.  See mi_edge_block2."""
+    _f32(a_bound), _f32(col_scale), _f32(bias), _f32(scat_out), _i32(scat_idx), _f32(scat_w), _f32(scat_amax)
+    N, K = w_hi.shape
+    check(lib().mi_edge_block2(E, N, K, _p(a_hi), _p(a_lo), _ld(a_hi), _p(a_bound), _p(w_hi), _p(w_lo), _ld(w_hi), _p(col_scale),
+                               _p(bias), _p(scat_out), _ld(scat_out), _p(scat_idx), _p(scat_w), _p(scat_amax), _stream()),
+          "mi_edge_block2")
+
+
 def weighted_field_sum(fields, weights, out):
     """out[b] = sum_k weights[k] * fields[k][b]  (<= 4 per-sample loss vectors).  See mi_weighted_field_sum."""
     for t in list(fields) + [out]:

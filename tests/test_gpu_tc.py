@@ -363,3 +363,74 @@ def test_node_chain_matches_separate_kernels(gold_full, num_atoms):
         again = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
     for u, v in zip(outs[0], again):
         assert torch.equal(u, v)
+
+
+# ---------------------------------------------------------------- CTA-pair per-edge blocks (csrc/mi_edge.cu)
+@pytest.mark.parametrize("crystals,spread", [(3, 0.0), (40, 0.0), (230, 3.0), (900, 0.0)])
+def test_edge_pair_blocks_vs_float64(crystals, spread):
+    """mi_edge_block1 -> mi_edge_block2 (tcgen05.mma.cta_group::2, both operands staged by TMA, a1 handed over as an fp16
+    pair scaled from an a-priori row bound) against float64 of cspnet.py:59-79: fc-like edge lists from one tile to many
+    waves, rows past the last 256-row tile, node rows spanning e^(+-3 sigma) in magnitude"""
+    import math
+    from matinvent_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    ns = torch.randint(1, 21, (crystals,), generator=g).tolist()
+    nn = sum(ns)
+    off = [0]
+    for n in ns:
+        off.append(off[-1] + n)
+    src = torch.cat([torch.arange(off[b], off[b + 1]).repeat_interleave(ns[b]) for b in range(crystals)])
+    dst = torch.cat([torch.arange(off[b], off[b + 1]).repeat(ns[b]) for b in range(crystals)])
+    E, H, F = src.numel(), 512, 128
+    K1 = 6 * F
+    # Fourier-like operand: sin / cos pairs of unit norm, in mi_edge_fourier's merged format (scaled 2^14, unscaled tail)
+    ang = (torch.rand(E, K1 // 2, generator=g) * 2 * math.pi).cuda()
+    phi = torch.cat([ang.sin(), ang.cos()], dim=1).contiguous()
+    ph = (phi * 2.0 ** 14).half()
+    pl = (phi * 2.0 ** 14 - ph.float()).half()
+    WF, W2, b2 = _rand(H, K1, seed=6) / K1 ** 0.5, _rand(H, H, seed=7) / H ** 0.5, 0.1 * _rand(H, seed=8)
+    pqr = (_rand(nn, 3 * H, seed=9) * torch.exp(spread * _rand(nn, 1, seed=10))).contiguous()
+    amax_pq = pqr.abs().amax(1).contiguous()
+
+    def rows(W):
+        hi, lo = torch.empty_like(W, dtype=torch.float16), torch.empty_like(W, dtype=torch.float16)
+        inv = torch.empty(W.shape[0], device="cuda")
+        ops.f16_split_rows(W, hi, lo, inv)
+        return hi, lo, inv
+
+    fh, fl, finv = rows(WF)
+    wh, wl, winv = rows(W2)
+    wfb = (math.sqrt(K1 / 2) * WF.norm(dim=1).max() * 1.001).reshape(1).contiguous()
+    a1 = torch.empty(2, E, H, device="cuda", dtype=torch.float16)
+    bound = torch.full((E,), float("nan"), device="cuda")
+    srci, dsti = src.int().cuda(), dst.int().cuda()
+    ops.edge_block1(E, ph, pl, fh, fl, finv, 2.0 ** -14, pqr[:, :H], pqr[:, H:2 * H], srci, dsti, amax_pq, wfb, a1[0], a1[1], bound)
+    z1 = phi.double() @ WF.double().t() + pqr[:, :H].double()[src.cuda()] + pqr[:, H:2 * H].double()[dst.cuda()]
+    r1 = torch.nn.functional.silu(z1)
+    assert bool((bound >= r1.abs().amax(1).float()).all())                    # it is a bound
+    e8 = torch.floor(torch.log2(bound)) - 14
+    got1 = (a1[0].double() + a1[1].double()) * torch.exp2(e8.double())[:, None]
+    err1 = float(((got1 - r1).abs().amax(1) / z1.abs().amax(1)).max())
+    slack = float((bound / r1.abs().amax(1).float().clamp_min(1e-30)).median())
+    print("edge block 1: E=%d worst row error %.2e (median bound / max = %.1f)" % (E, err1, slack))
+    assert err1 < 6e-6, err1
+    # block 2 on block 1's own output: means over the source node's edges
+    seg = torch.repeat_interleave(torch.arange(nn), torch.tensor([n for n in ns for _ in range(n)]))
+    w = (1.0 / torch.tensor([n for n in ns for _ in range(n)], dtype=torch.float32))[seg].cuda()
+    out = torch.zeros(nn, 2 * H, device="cuda")
+    agg, amax = out[:, H:], torch.zeros(nn, device="cuda")
+    ops.edge_block2(E, a1[0], a1[1], bound, wh, wl, winv, b2, agg, srci, w, amax)
+    y = torch.nn.functional.silu(got1 @ W2.double().t() + b2.double())
+    ref = torch.zeros(nn, H, dtype=torch.float64, device="cuda").index_add_(0, seg.cuda(), y) * \
+        (1.0 / torch.tensor(ns, dtype=torch.float64).repeat_interleave(torch.tensor(ns))).cuda()[:, None]
+    err2 = float(((agg.double() - ref).abs().amax(1) / ref.abs().amax(1)).max())
+    print("edge block 2: worst row error %.2e" % err2)
+    assert err2 < 8e-6, err2
+    assert float(out[:, :H].abs().max()) == 0.0
+    assert bool((amax >= ref.abs().amax(1).float() * (1 - 1e-5)).all())
+    # against the single-CTA kernels on the same operands (same format, same products): rounding-level agreement
+    a_ref = torch.empty(E, H, device="cuda")
+    am = torch.zeros(E, device="cuda")
+    ops.tc_gemm_presplit(ph, pl, fh, fl, a_ref, M=E, alpha=2.0 ** -14, col_scale=finv, flags=ops.TC_MERGED,
+                         gathers=[(pqr[:, :H], srci), (pqr[:, H:2 * H], dsti)], act=ops.ACT_SILU, amax_out=am)
+    assert float(((got1 - a_ref.double()).abs().amax(1) / z1.abs().amax(1)).max()) < 4e-6
