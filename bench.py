@@ -122,6 +122,10 @@ class ClockSampler:
                     power_w_max=max(float(r[3]) for r in rows), samples=len(rows))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of edge_pair_kernel<0> at the default workload, from the committed
+# ncu --set full capture (profiles/r2_edge_pair_ncu_raw.csv); None until that capture exists
+PAIR_TRAFFIC = None
+
 WORKLOAD = "DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU"
 
 
@@ -354,10 +358,12 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = fl_g1 / (t_g1 * 1e-6) / 1e12
     ach_pair = fl_pair / t_pair / 1e12
-    kname = "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)"
+    pair = dec.pair_mode(False, merged)
+    kname = ("edge_pair_kernel<0> (tcgen05.mma.cta_group::2, split-precision FP16 x3, both operands staged by TMA)" if pair else
+             "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)")
     # DRAM traffic of this launch from the committed ncu --set full capture of the default workload
     # (profiles/r1b_tc_gemm_ncu_raw.csv, tc_gemm_kernel<256,1,1,1>: dram__bytes_read.sum 123.3 MB + dram__bytes_write.sum 35.6 MB)
-    traffic = 158.9e6 if (dec.use_tc and merged and g.E == 34445) else None
+    traffic = PAIR_TRAFFIC if (pair and g.E == 34445) else None
     roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM 1 (Phi.W_F^T + 2 gathered rows + SiLU), the largest launch",
                     achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
                     flop_per_launch=fl_g1, us_per_launch=t_g1,
@@ -367,7 +373,8 @@ def main():
                          "product (x = hi + lo), so the ceiling of frac is 1/3 (1e-4 parity over 2000 chained forwards rules out "
                          "plain TF32/BF16/FP16 inputs); tiles: %s; edge GEMM pair (this launch + the K=512 one): %.1f TFLOP/s, "
                          "share of step = %.2f"
-                         % ("128x256, one accumulator" if merged else "128x128, main + correction accumulators", ach_pair,
+                         % ("256x256 per CTA pair, one accumulator" if pair else "128x256, one accumulator" if merged else
+                            "128x128, main + correction accumulators", ach_pair,
                             2 * HP["num_layers"] * t_pair / (ms / 1e3 / args.steps / T)),
                     mma_tflops=3 * ach, frac_mma_of_peak=3 * ach / peak_tf, us_gemm1=t_g1, us_gemm2=t_g2)
     # the edge-scatter (segment-mean) kernel against the HBM roofline, in isolation, L2 flushed between launches

@@ -44,14 +44,16 @@ constexpr int EPI_WARPS = 8, EPI_WARP0 = 2, THREADS = (EPI_WARP0 + EPI_WARPS) * 
 constexpr int RING_BYTES = S * OPB, BAR_BYTES = 256;
 constexpr int OFF_BAR = RING_BYTES, OFF_PART = OFF_BAR + BAR_BYTES;
 constexpr int CLUSTER = 4, PARTS = 2 * CLUSTER;               // partial LayerNorm statistics per row: 4 CTAs x 2 column groups
-constexpr int SMEM_BYTES = OFF_PART + TM * PARTS * 8;
+constexpr int OFF_CST = OFF_PART + TM * PARTS * 8;            // this CTA's column slice of b_n1 | b_n2 | gamma | beta
+constexpr int SMEM_BYTES = OFF_CST + 4 * TN * 4;
 static_assert(SMEM_BYTES <= 232448, "does not fit the SM");
-static_assert((3 * S + 4) * 8 + 8 <= BAR_BYTES, "barrier block too small");
+static_assert((3 * S + 5) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 constexpr uint32_t ACC_COLS = 2 * TN, TMEM_COLS = 2 * ACC_COLS;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 struct Params {
     int M, n_phases;
+    int rows;                                // rows per cluster (<= TM, multiple of 8): chosen so that the row blocks fill the machine
     float* agg; int ld_agg; const float* amax_agg; int zero_agg;
     __half* xs_hi; __half* xs_lo;            // [M, H] operand of phase 0 (agg) and of phase 2 (LN(h))
     __half* ys_hi; __half* ys_lo;            // [M, H] operand of phase 1 (an1)
@@ -62,10 +64,19 @@ struct Params {
     const float* cb; int ld_cb; const int* node_graph; float* pqr; int ld_pqr; float* amax_next;
 };
 
+#ifdef MI_NODE_TRACE
+// Developer instrumentation (scripts/trace_node.py builds a separate library with -DMI_NODE_TRACE; never in the product
+// build): per-CTA SM clock stamps of the phases.
+constexpr int NT_SLOTS = 32;
+__device__ long long g_ntrace[160 * NT_SLOTS];
+#define NTRACE(slot) do { g_ntrace[blockIdx.x * NT_SLOTS + (slot)] = clock64(); } while (0)
+#else
+#define NTRACE(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ void cluster_sync_all() {
     // every thread of the four CTAs: global writes of this phase (generic proxy) -> visible to the peers' loads, including
     // their TMA loads (async proxy)
-    __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -101,11 +112,11 @@ __device__ __forceinline__ void st8f(float* p, const float* v) {
 }
 
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1)
-node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
-                  const __grid_constant__ CUtensorMap mapYh, const __grid_constant__ CUtensorMap mapYl,
-                  const __grid_constant__ CUtensorMap mapW0h, const __grid_constant__ CUtensorMap mapW0l,
-                  const __grid_constant__ CUtensorMap mapW1h, const __grid_constant__ CUtensorMap mapW1l,
-                  const __grid_constant__ CUtensorMap mapW2h, const __grid_constant__ CUtensorMap mapW2l, const Params p) {
+node_chain_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                  const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
+                  const __grid_constant__ CUtensorMap mapW2, const Params p) {
+    // every map covers an fp16 (hi, lo) PAIR (3-D, planes = hi / lo): one TMA operation per operand and k-block.  The
+    // producer is bound by operations (~170 cycles each), not bytes, at these tile sizes.
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* ring = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -114,12 +125,15 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
     uint64_t* op_empty = bars + 2 * S;        // [S] MMAs done with the slot
     uint64_t* acc_full = bars + 3 * S;        // [2]
     uint64_t* acc_empty = acc_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 4);
+    uint64_t* stat_bar = acc_full + 4;        // partial LayerNorm statistics of all four CTAs have landed (st.async)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 5);
+    float* cst = reinterpret_cast<float*>(smem + OFF_CST);
     float2* part = reinterpret_cast<float2*>(smem + OFF_PART);      // [TM][PARTS] partial (mean, M2) of the LayerNorm rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) NTRACE(0);
     const int crank = (int)(blockIdx.x % CLUSTER);               // rank in the cluster = column slice
-    const int m0 = (int)(blockIdx.x / CLUSTER) * TM;             // the cluster's row block
+    const int m0 = (int)(blockIdx.x / CLUSTER) * p.rows;         // the cluster's row block: R <= TM rows (the MMA tile's other rows are not used)
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();
@@ -132,13 +146,12 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             mbar_init(&acc_full[b], 1);
             mbar_init(&acc_empty[b], EPI_WARPS);
         }
+        mbar_init(stat_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapXh) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapXl) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0h) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0l) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW0) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -148,9 +161,12 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) NTRACE(1);
+    const bool tr = threadIdx.x == EPI_WARP0 * 32;                 // the thread that stamps the epilogue side
+    (void)tr;
 
-    // Cluster barriers, the same sequence in every thread:  B0 after the prologue, B1 after phase 0, and with a LayerNorm
-    // phase B2 (partial statistics exchanged) and B3 (LN(h) operand written) before phase 2.
+    // Cluster barriers, the same sequence in every thread:  B0 after the prologue, B1 after phase 0 and, with a LayerNorm
+    // phase, B2 (LN(h) operand written) before phase 2.
     if (warp == 0) {
         // ===================== TMA producer =====================
         uint32_t g = 0;                                            // k-blocks through the ring so far
@@ -158,10 +174,8 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
             const int ntl = phx == 2 ? 3 : 1;
             const uint32_t total = (uint32_t)(ntl * NKB);
             const uint32_t pre = total < (uint32_t)S ? total : (uint32_t)S;
-            const CUtensorMap* mAh = phx == 1 ? &mapYh : &mapXh;
-            const CUtensorMap* mAl = phx == 1 ? &mapYl : &mapXl;
-            const CUtensorMap* mWh = phx == 0 ? &mapW0h : (phx == 1 ? &mapW1h : &mapW2h);
-            const CUtensorMap* mWl = phx == 0 ? &mapW0l : (phx == 1 ? &mapW1l : &mapW2l);
+            const CUtensorMap* mA = phx == 1 ? &mapY : &mapX;
+            const CUtensorMap* mW = phx == 0 ? &mapW0 : (phx == 1 ? &mapW1 : &mapW2);
             auto issue_w = [&](uint32_t loc) {
                 const uint32_t gi = g + loc;
                 const int s = (int)(gi % (uint32_t)S);
@@ -170,32 +184,27 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                 mbar_wait(&op_empty[s], ((gi / (uint32_t)S) & 1) ^ 1);
                 uint8_t* st = ring + s * OPB;
                 mbar_expect_tx(&w_full[s], 2 * W_H);
-                tma_load_2d(st + 2 * A_H, mWh, &w_full[s], kb * TK, n0);
-                tma_load_2d(st + 2 * A_H + W_H, mWl, &w_full[s], kb * TK, n0);
+                tma_load_3d(st + 2 * A_H, mW, &w_full[s], kb * TK, n0, 0);          // W_hi | W_lo
             };
             // the weights do not depend on the previous phase: the first ring-full of W tiles crosses the barrier
             if (lane == 0)
                 for (uint32_t loc = 0; loc < pre; ++loc) issue_w(loc);
             __syncwarp();
-            cluster_sync_all();
-            if (phx == 2) cluster_sync_all();
+            cluster_sync_all();                                    // B0 / B1 / B2
             if (lane == 0) {
                 for (uint32_t loc = 0; loc < total; ++loc) {
                     if (loc >= pre) issue_w(loc);
                     const int s = (int)((g + loc) % (uint32_t)S);
                     const int kb = (int)(loc % (uint32_t)NKB);
                     uint8_t* st = ring + s * OPB;
-                    mbar_expect_tx(&a_full[s], 2 * A_H);
-                    tma_load_2d(st, mAh, &a_full[s], kb * TK, m0);
-                    tma_load_2d(st + A_H, mAl, &a_full[s], kb * TK, m0);
+                    mbar_expect_tx(&a_full[s], (uint32_t)(2 * p.rows * TK * 2));
+                    tma_load_3d(st, mA, &a_full[s], kb * TK, m0, 0);                // A_hi (rows x 64 B) | A_lo right behind it
                 }
                 if (phx + 1 < p.n_phases) {
-                    const CUtensorMap* nAh = phx == 0 ? &mapYh : &mapXh;
-                    const CUtensorMap* nWh = phx == 0 ? &mapW1h : &mapW2h;
-                    const CUtensorMap* nWl = phx == 0 ? &mapW1l : &mapW2l;
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(nAh) : "memory");
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(nWh) : "memory");
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(nWl) : "memory");
+                    const CUtensorMap* nA = phx == 0 ? &mapY : &mapX;
+                    const CUtensorMap* nW = phx == 0 ? &mapW1 : &mapW2;
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(nA) : "memory");
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(nW) : "memory");
                 }
             }
             __syncwarp();
@@ -206,8 +215,7 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         uint32_t g = 0, gt = 0;
         for (int phx = 0; phx < p.n_phases; ++phx) {
             const int ntl = phx == 2 ? 3 : 1;
-            cluster_sync_all();
-            if (phx == 2) cluster_sync_all();
+            cluster_sync_all();                                    // B0 / B1 / B2
             if (lane == 0) {
                 for (int tl = 0; tl < ntl; ++tl, ++gt) {
                     const uint32_t ab = gt & 1;
@@ -218,10 +226,12 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         const int s = (int)(g % (uint32_t)S);
                         const uint32_t par = (g / (uint32_t)S) & 1;
                         mbar_wait(&w_full[s], par);
+                        if (kb == 0 && tl == 0) NTRACE(17 + 3 * phx);
                         mbar_wait(&a_full[s], par);
+                        if (kb == 0 && tl == 0) NTRACE(18 + 3 * phx);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t st = smem_u32(ring + s * OPB);
-                        const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + A_H);
+                        const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + (uint32_t)(p.rows * TK * 2));
                         const uint64_t d_whi = umma_desc(st + 2 * A_H), d_wlo = umma_desc(st + 2 * A_H + W_H);
 #pragma unroll
                         for (int k = 0; k < TK / 16; ++k) {
@@ -233,6 +243,7 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                         umma_commit(&op_empty[s]);
                     }
                     umma_commit(&acc_full[ab]);
+                    if (tl == ntl - 1) NTRACE(19 + 3 * phx);
                 }
             } else {
                 g += (uint32_t)(ntl * NKB);
@@ -243,31 +254,51 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
         }
     } else {
         // ===================== prologue + epilogue warps (w2..9) =====================
+        // Every stage is a SHORT ROLLED LOOP over 16-column groups.  A launch runs each stage once, so the first version's
+        // straight-line epilogues (6 000 instructions, 97 KB of code) ran at instruction-fetch speed, 5-8 cycles per warp
+        // instruction (profiles/r2_node_trace.md).  The operands gathered from global memory are fetched one group ahead.
         const int t = threadIdx.x - EPI_WARP0 * 32;           // 0..255
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
         const int cg = (warp - EPI_WARP0) >> 2;               // column group: 64 of the tile's 128 columns
         const int rl = q * 32 + lane;                         // row inside the block: the TMEM lane this thread owns
         const int row = m0 + rl;
-        const bool ok = row < p.M;
+        const bool ok = rl < p.rows && row < p.M;
         const float wb_l1 = __ldg(p.bounds), b1_max = __ldg(p.bounds + 1);
+        const float ln_bound = p.n_phases == 3 ? __ldg(p.bounds + 2) : 1.0f;
 
+        // per-column constants of this CTA's slice -> shared memory (the cluster barriers invalidate L1: a global load per
+        // group would pay an L2 round trip every time)
+        if (t < TN) {
+            cst[t] = __ldg(p.bn1 + crank * TN + t);
+            cst[TN + t] = __ldg(p.bn2 + crank * TN + t);
+            if (p.n_phases == 3) {
+                cst[2 * TN + t] = __ldg(p.ln_g + crank * TN + t);
+                cst[3 * TN + t] = __ldg(p.ln_b + crank * TN + t);
+            }
+        }
         // ---- prologue: this CTA's 128-column slice of agg -> fp16 (hi, lo) pairs, rows scaled from their maxima
-        {
-            float4 vv[16];
+#pragma unroll 1
+        for (int pg = 0; pg < 4; ++pg) {
+            float4 vv[4];
+            float am[4];
 #pragma unroll
-            for (int ps = 0; ps < 16; ++ps) {
-                const int r = m0 + ps * 8 + (t >> 5);
-                vv[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < p.M) vv[ps] = __ldcg(reinterpret_cast<const float4*>(p.agg + (long long)r * p.ld_agg + crank * TN + (t & 31) * 4));
+            for (int u = 0; u < 4; ++u) {
+                const int r = m0 + (pg * 4 + u) * 8 + (t >> 5);
+                vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                am[u] = 0.f;
+                if (r < p.M && (pg * 4 + u) * 8 + (t >> 5) < p.rows) {
+                    vv[u] = __ldcg(reinterpret_cast<const float4*>(p.agg + (long long)r * p.ld_agg + crank * TN + (t & 31) * 4));
+                    am[u] = __ldg(p.amax_agg + r);
+                }
             }
 #pragma unroll
-            for (int ps = 0; ps < 16; ++ps) {
-                const int r = m0 + ps * 8 + (t >> 5);
-                if (r >= p.M) continue;
-                const float sc = pow2f(-exp8(__ldg(p.amax_agg + r)));
+            for (int u = 0; u < 4; ++u) {
+                const int r = m0 + (pg * 4 + u) * 8 + (t >> 5);
+                if (r >= p.M || (pg * 4 + u) * 8 + (t >> 5) >= p.rows) continue;
+                const float sc = pow2f(-exp8(am[u]));
                 uint2 hh, ll;
-                split2<0>(vv[ps].x * sc, vv[ps].y * sc, hh.x, ll.x);
-                split2<0>(vv[ps].z * sc, vv[ps].w * sc, hh.y, ll.y);
+                split2<0>(vv[u].x * sc, vv[u].y * sc, hh.x, ll.x);
+                split2<0>(vv[u].z * sc, vv[u].w * sc, hh.y, ll.y);
                 const long long o = (long long)r * H + crank * TN + (t & 31) * 4;
                 *reinterpret_cast<uint2*>(p.xs_hi + o) = hh;
                 *reinterpret_cast<uint2*>(p.xs_lo + o) = ll;
@@ -275,41 +306,42 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     *reinterpret_cast<float4*>(p.agg + (long long)r * p.ld_agg + crank * TN + (t & 31) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        if (tr) NTRACE(2);
         cluster_sync_all();                                    // B0
+        if (tr) NTRACE(3);
 
         const float am_agg = ok ? __ldg(p.amax_agg + row) : 0.f;
         const float bound1 = ok ? an1_bound(am_agg, __ldcg(p.amax_pqr + row), wb_l1, b1_max) : 0.f;
         const int e_agg = exp8(am_agg), e_an1 = exp8(bound1);
-        uint32_t v[32], w[32];
+        const int cbase = crank * TN + cg * 64;               // first of this thread's 64 columns (phases 0 and 1)
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
+        uint32_t v[16], w[16];
+        float rn[16], r[16];
 
         // ---- phase 0 epilogue: an1 = silu(acc + R + b_n1), written as the pre-split operand of phase 1
         {
             const float rowsc = pow2f(e_agg), osc = pow2f(-e_an1);
-            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
+            const float* rrow = p.R + (long long)(ok ? row : 0) * p.ld_r + cbase;
+            ldcg8(rrow, rn);
+            ldcg8(rrow + 8, rn + 8);
             mbar_wait(&acc_full[0], 0);
+            if (tr) NTRACE(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-                const int n = crank * TN + cg * 64 + cc * 32;
-                tmem_ld32(tb + (uint32_t)(cc * 32), v);
-                tmem_ld32(tb + (uint32_t)(cc * 32) + TN, w);
-                float r[32];
+            for (int it = 0; it < 4; ++it) {
+                tmem_ld16(trow + (uint32_t)(it * 16), v);
+                tmem_ld16(trow + (uint32_t)(it * 16) + TN, w);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0.f;
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) ldcg8(p.R + (long long)row * p.ld_r + n + j, r + j);
+                for (int j = 0; j < 16; ++j) r[j] = rn[j];
+                if (it + 1 < 4) {
+                    ldcg8(rrow + (it + 1) * 16, rn);
+                    ldcg8(rrow + (it + 1) * 16 + 8, rn + 8);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[0]);
-                }
-                uint32_t hi[16], lo[16];
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bn1 + n + j));
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(cst + cg * 64 + it * 16 + j);
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float a[4];
 #pragma unroll
@@ -321,71 +353,87 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
                     split2<0>(a[2], a[3], hi[j / 2 + 1], lo[j / 2 + 1]);
                 }
                 if (ok) {
-                    const long long o = (long long)row * H + n;
-                    st8(p.ys_hi + o, hi); st8(p.ys_hi + o + 16, hi + 8);
-                    st8(p.ys_lo + o, lo); st8(p.ys_lo + o + 16, lo + 8);
+                    const long long o = (long long)row * H + cbase + it * 16;
+                    st8(p.ys_hi + o, hi);
+                    st8(p.ys_lo + o, lo);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[0]);
         }
+        if (tr) NTRACE(5);
         cluster_sync_all();                                    // B1
+        if (tr) NTRACE(6);
 
-        // ---- phase 1 epilogue: h = h_in + silu(acc + b_n2); the finished rows are normalised in place (next LayerNorm)
+        // ---- phase 1 epilogue: h = h_in + silu(acc + b_n2); the finished rows stay in TMEM (over their accumulator) for
+        // the two LayerNorm passes that follow (next layer's LayerNorm)
         {
             const float rowsc = pow2f(e_an1);
-            const uint32_t tb = tmem_base + ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
-            float x[64];
+            const uint32_t tb = trow + ACC_COLS;
+            const float* hrow = p.h_in + (long long)(ok ? row : 0) * p.ld_hin + cbase;
+            ldcg8(hrow, rn);
+            ldcg8(hrow + 8, rn + 8);
             mbar_wait(&acc_full[1], 0);
+            if (tr) NTRACE(7);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float sum = 0.f;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                tmem_ld16(tb + (uint32_t)(it * 16), v);
+                tmem_ld16(tb + (uint32_t)(it * 16) + TN, w);
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int n = crank * TN + cg * 64 + cc * 32;
-                tmem_ld32(tb + (uint32_t)(cc * 32), v);
-                tmem_ld32(tb + (uint32_t)(cc * 32) + TN, w);
-                float r[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0.f;
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) ldcg8(p.h_in + (long long)row * p.ld_hin + n + j, r + j);
+                for (int j = 0; j < 16; ++j) r[j] = rn[j];
+                if (it + 1 < 4) {
+                    ldcg8(hrow + (it + 1) * 16, rn);
+                    ldcg8(hrow + (it + 1) * 16 + 8, rn + 8);
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[1]);
-                }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bn2 + n + j));
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(cst + TN + cg * 64 + it * 16 + j);
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float acc = fmaf(__uint_as_float(w[j + u]), LO_UNSCALE, __uint_as_float(v[j + u]));
-                        x[cc * 32 + j + u] = r[j + u] + silu_fast(rowsc * acc + bb[u]);
+                        r[j + u] = (ok ? r[j + u] : 0.f) + silu_fast(rowsc * acc + bb[u]);
+                        sum += r[j + u];
                     }
                 }
                 if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) st8f(p.h + (long long)row * p.ld_h + n + j, x + cc * 32 + j);
+                    float* o = p.h + (long long)row * p.ld_h + cbase + it * 16;
+                    st8f(o, r);
+                    st8f(o + 8, r + 8);
                 }
+                if (p.n_phases == 3) tmem_st16(tb + (uint32_t)(it * 16), r);
             }
             if (p.n_phases == 3) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 // partial statistics of this thread's 64 columns -> every CTA of the cluster (distributed shared memory)
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < 64; ++j) s += x[j];
-                const float mp = s * (1.0f / 64.0f);
+                const float mp = sum * (1.0f / 64.0f);
                 float m2 = 0.f;
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {
+                    tmem_ld16(tb + (uint32_t)(it * 16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 64; ++j) m2 = fmaf(x[j] - mp, x[j] - mp, m2);
-                const uint32_t laddr = smem_u32(part + rl * PARTS + crank * 2 + cg);
+                    for (int j = 0; j < 16; ++j) m2 = fmaf(__uint_as_float(v[j]) - mp, __uint_as_float(v[j]) - mp, m2);
+                }
+                // st.async: the data lands in the peer's shared memory and counts on the peer's barrier: no cluster barrier,
+                // and nothing waits for the global stores of h above
+                const uint32_t laddr = smem_u32(part + rl * PARTS + crank * 2 + cg), lbar = smem_u32(stat_bar);
+                if (tr) mbar_expect_tx(stat_bar, (uint32_t)(EPI_WARPS * 32 * CLUSTER * 8));
 #pragma unroll
                 for (int c = 0; c < CLUSTER; ++c) {
-                    uint32_t raddr;
+                    uint32_t raddr, rbar;
                     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(c));
-                    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(mp), "f"(m2) : "memory");
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(lbar), "r"(c));
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                                 ::"r"(raddr), "f"(mp), "f"(m2), "r"(rbar) : "memory");
                 }
-                cluster_sync_all();                            // B2
+                if (tr) NTRACE(8);
+                mbar_wait(stat_bar, 0);
+                if (tr) NTRACE(9);
                 float mean = 0.f;
                 float2 pp[PARTS];
 #pragma unroll
@@ -398,75 +446,91 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < PARTS; ++c) M2 += pp[c].y + 64.0f * (pp[c].x - mean) * (pp[c].x - mean);
                 const float rstd = 1.0f / sqrtf(M2 * (1.0f / (float)H) + p.ln_eps);
-                const float osc = pow2f(-exp8(__ldg(p.bounds + 2)));
+                const float osc = pow2f(-exp8(ln_bound));
+#pragma unroll 1
+                for (int it = 0; it < 4; ++it) {
+                    tmem_ld16(tb + (uint32_t)(it * 16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int n = crank * TN + cg * 64 + cc * 32;
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + n + j));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + n + j));
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(cst + 2 * TN + cg * 64 + it * 16 + j);
+                        const float4 b4 = *reinterpret_cast<const float4*>(cst + 3 * TN + cg * 64 + it * 16 + j);
                         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
                         float a[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) a[u] = ((x[cc * 32 + j + u] - mean) * rstd * gg[u] + bb[u]) * osc;
+                        for (int u = 0; u < 4; ++u) a[u] = ((__uint_as_float(v[j + u]) - mean) * rstd * gg[u] + bb[u]) * osc;
                         split2<0>(a[0], a[1], hi[j / 2], lo[j / 2]);
                         split2<0>(a[2], a[3], hi[j / 2 + 1], lo[j / 2 + 1]);
                     }
                     if (ok) {
-                        const long long o = (long long)row * H + n;
-                        st8(p.xs_hi + o, hi); st8(p.xs_hi + o + 16, hi + 8);
-                        st8(p.xs_lo + o, lo); st8(p.xs_lo + o + 16, lo + 8);
+                        const long long o = (long long)row * H + cbase + it * 16;
+                        st8(p.xs_hi + o, hi);
+                        st8(p.xs_lo + o, lo);
                     }
                 }
-                cluster_sync_all();                            // B3
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[1]);
+            if (p.n_phases == 3) {
+                if (tr) NTRACE(10);
+                cluster_sync_all();                            // B2
+                if (tr) NTRACE(11);
             }
         }
 
         // ---- phase 2 epilogue: [P'|Q|R] = acc + [C_b|0|0][crystal of the row]; row maxima for the consumers' bounds
         if (p.n_phases == 3) {
-            const float rowsc = pow2f(exp8(__ldg(p.bounds + 2)));
+            const float rowsc = pow2f(exp8(ln_bound));
             const int gi = ok ? __ldg(p.node_graph + row) : 0;
             float rmax = 0.f;
 #pragma unroll 1
             for (int tl = 0; tl < 3; ++tl) {
                 const uint32_t gt = 2u + (uint32_t)tl;
                 const uint32_t ab = gt & 1;
-                const uint32_t tb = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 64);
+                const uint32_t tb = trow + ab * ACC_COLS;
+                const int ncol = (crank * 3 + tl) * TN + cg * 64;
+                const float* crow = p.cb + (long long)gi * p.ld_cb + ncol;     // [C_b|0|0] of the row's crystal
+                ldnc8(crow, rn);
+                ldnc8(crow + 8, rn + 8);
                 mbar_wait(&acc_full[ab], (gt >> 1) & 1);
+                if (tr) NTRACE(12 + tl);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int n = (crank * 3 + tl) * TN + cg * 64 + cc * 32;
-                    tmem_ld32(tb + (uint32_t)(cc * 32), v);
-                    tmem_ld32(tb + (uint32_t)(cc * 32) + TN, w);
-                    float r[32];
+                for (int it = 0; it < 4; ++it) {
+                    tmem_ld16(tb + (uint32_t)(it * 16), v);
+                    tmem_ld16(tb + (uint32_t)(it * 16) + TN, w);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) ldnc8(p.cb + (long long)gi * p.ld_cb + n + j, r + j);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cc == 1) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+                    for (int j = 0; j < 16; ++j) r[j] = rn[j];
+                    if (it + 1 < 4) {
+                        ldnc8(crow + (it + 1) * 16, rn);
+                        ldnc8(crow + (it + 1) * 16 + 8, rn + 8);
                     }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const float acc = fmaf(__uint_as_float(w[j]), LO_UNSCALE, __uint_as_float(v[j]));
                         r[j] = rowsc * acc + r[j];
                         rmax = fmaxf(rmax, fabsf(r[j]));
                     }
                     if (ok) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) st8f(p.pqr + (long long)row * p.ld_pqr + n + j, r + j);
+                        float* o = p.pqr + (long long)row * p.ld_pqr + ncol + it * 16;
+                        st8f(o, r);
+                        st8f(o + 8, r + 8);
                     }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
             if (ok && p.amax_next) atomicMax(reinterpret_cast<unsigned*>(p.amax_next + row), __float_as_uint(rmax));
+            if (tr) NTRACE(15);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) NTRACE(16);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -474,6 +538,13 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapXh, const __grid_consta
 }
 
 }  // namespace
+
+#ifdef MI_NODE_TRACE
+extern "C" int mi_node_trace_read(long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_ntrace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 extern "C" int mi_node_chain(int M, int Hdim, int n_phases, float* agg, int ld_agg, const float* amax_agg, int zero_agg,
                              void* xs_hi, void* xs_lo, void* ys_hi, void* ys_lo, const void* wb_hi, const void* wb_lo, int ld_wb,
@@ -498,21 +569,13 @@ extern "C" int mi_node_chain(int M, int Hdim, int n_phases, float* agg, int ld_a
                  "operands need 32-byte aligned rows");
     int rc = mi_tc_get_encode();
     if (rc != MI_OK) return rc;
-    CUtensorMap mXh, mXl, mYh, mYl, mW0h, mW0l, mW1h, mW1l, mW2h, mW2l;
-    if ((rc = mi_tc_make_map(&mXh, xs_hi, M, H, H, TM, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mXl, xs_lo, M, H, H, TM, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mYh, ys_hi, M, H, H, TM, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mYl, ys_lo, M, H, H, TM, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mW0h, wb_hi, H, H, ld_wb, TN, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mW0l, wb_lo, H, H, ld_wb, TN, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mW1h, w2_hi, H, H, H, TN, true)) != MI_OK) return rc;
-    if ((rc = mi_tc_make_map(&mW1l, w2_lo, H, H, H, TN, true)) != MI_OK) return rc;
+    CUtensorMap mX, mY, mW0, mW1, mW2;
+    if ((rc = mi_tc_make_map_pair(&mW0, wb_hi, wb_lo, H, H, ld_wb, TN)) != MI_OK) return rc;
+    if ((rc = mi_tc_make_map_pair(&mW1, w2_hi, w2_lo, H, H, H, TN)) != MI_OK) return rc;
     if (n_phases == 3) {
-        if ((rc = mi_tc_make_map(&mW2h, wpqr_hi, 3 * H, H, H, TN, true)) != MI_OK) return rc;
-        if ((rc = mi_tc_make_map(&mW2l, wpqr_lo, 3 * H, H, H, TN, true)) != MI_OK) return rc;
+        if ((rc = mi_tc_make_map_pair(&mW2, wpqr_hi, wpqr_lo, 3 * H, H, H, TN)) != MI_OK) return rc;
     } else {
-        mW2h = mW1h;
-        mW2l = mW1l;
+        mW2 = mW1;
     }
     Params p = {};
     p.M = M; p.n_phases = n_phases;
@@ -522,14 +585,36 @@ extern "C" int mi_node_chain(int M, int Hdim, int n_phases, float* agg, int ld_a
     p.bn2 = bn2; p.h_in = h_in; p.ld_hin = ld_hin; p.h = h; p.ld_h = ld_h;
     p.ln_g = ln_g; p.ln_b = ln_b; p.ln_eps = ln_eps;
     p.cb = cb; p.ld_cb = ld_cb; p.node_graph = node_graph; p.pqr = pqr; p.ld_pqr = ld_pqr; p.amax_next = amax_next;
-    static bool attr = false;
-    if (!attr) {
+    // Rows per cluster: the stages of this kernel are latency-bound per CTA (epilogue traffic, operand ingest), so the row
+    // blocks are made as short as the machine allows: as many clusters as can be co-resident, 8-row granularity.
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
         MI_CUDA(cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CLUSTER * 64);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, node_chain_kernel, &cfg) != cudaSuccess || nc <= 0) {
+            cudaGetLastError();
+            nc = 21;
+        }
+        max_clusters = nc;
     }
-    const int row_blocks = mi_div_up(M, TM);
-    node_chain_kernel<<<row_blocks * CLUSTER, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mXh, mXl, mYh, mYl, mW0h, mW0l, mW1h,
-                                                                                          mW1l, mW2h, mW2l, p);
+    int R = (mi_div_up(M, max_clusters) + 7) / 8 * 8;
+    const char* force_r = getenv("MI_NODE_ROWS");
+    if (force_r) R = atoi(force_r);
+    if (R > TM) R = TM;
+    if (R < 8) R = 8;
+    p.rows = R;
+    if ((rc = mi_tc_make_map_pair(&mX, xs_hi, xs_lo, M, H, H, R)) != MI_OK) return rc;
+    if ((rc = mi_tc_make_map_pair(&mY, ys_hi, ys_lo, M, H, H, R)) != MI_OK) return rc;
+    const int row_blocks = mi_div_up(M, R);
+    node_chain_kernel<<<row_blocks * CLUSTER, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mX, mY, mW0, mW1, mW2, p);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

@@ -768,9 +768,34 @@ int dispatch_tc_scatter(int epi_mode, int M, int N, int K, const void* A, int ld
     return launch_tc<256, 18, 1, 0>(M, N, K, A, nullptr, lda, W_hi, W_lo, ldw, s, p);
 }
 
+// (hi, lo) operand pair as ONE 3-D map [2 planes, rows, cols]: a single TMA operation lands the hi tile followed by the lo
+// tile (box = [2, box_rows, 32 columns]); lo must follow hi in memory by a multiple of 16 bytes
+int make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld, int box_rows) {
+    const long long plane = (const char*)lo - (const char*)hi;
+    if (plane <= 0 || (plane & 15)) {
+        mi_set_error_("operand pair: lo must follow hi by a positive multiple of 16 bytes (got %lld)", plane);
+        return MI_ERR_ARG;
+    }
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+    cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane};
+    cuuint32_t box[3] = {(cuuint32_t)TK, (cuuint32_t)box_rows, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(hi), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mi_set_error_("cuTensorMapEncodeTiled failed (%d) for the pair [2,%lld,%lld] ld %lld plane %lld", (int)r, rows, cols, ld, plane);
+        return MI_ERR_CUDA;
+    }
+    return MI_OK;
+}
+
 }  // namespace
 
 int mi_tc_get_encode() { return get_encode(); }
+int mi_tc_make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld, int box_rows) {
+    return make_map_pair(map, hi, lo, rows, cols, ld, box_rows);
+}
 int mi_tc_make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, bool half) {
     return make_map(map, base, rows, cols, ld, box_rows, half);
 }

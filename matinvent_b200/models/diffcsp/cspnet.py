@@ -66,8 +66,9 @@ class _Workspace:
         self.hn_hi = torch.empty(N, H, device=dev, dtype=torch.float16)      # LN(h) as a pre-split tensor-core operand
         self.hn_lo = torch.empty(N, H, device=dev, dtype=torch.float16)
         # operand pairs written by the node chain's epilogues (mi_node_chain): xs = split(agg) / split(LN(h)), ys = split(an1)
-        self.xs = (torch.empty(N, H, device=dev, dtype=torch.float16), torch.empty(N, H, device=dev, dtype=torch.float16))
-        self.ys = (torch.empty(N, H, device=dev, dtype=torch.float16), torch.empty(N, H, device=dev, dtype=torch.float16))
+        # (hi and lo are the two planes of ONE allocation: a single 3-D TMA operation loads both)
+        self.xs = tuple(torch.empty(2, N, H, device=dev, dtype=torch.float16))
+        self.ys = tuple(torch.empty(2, N, H, device=dev, dtype=torch.float16))
         self.a1 = [buf(E, H) for _ in range(nl)]
         self.a2 = buf(E, H)
         self.an1 = [buf(N, H) for _ in range(nl)]
@@ -234,8 +235,8 @@ class CSPNet(nn.Module):
         if self._tc_version == ver and self._flat_hi is not None:
             return
         if self._flat_hi is None:
-            self._flat_hi = torch.empty_like(self.flat.data, dtype=torch.float16)
-            self._flat_lo = torch.empty_like(self.flat.data, dtype=torch.float16)
+            # hi and lo are the two planes of one allocation (operand pairs are loaded by single 3-D TMA operations)
+            self._flat_hi, self._flat_lo = torch.empty(2, self.flat.numel(), device=self.flat.device, dtype=torch.float16)
             self._hi = {k: self._flat_hi[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
             self._lo = {k: self._flat_lo[o:o + n].view(shape) for k, (o, n, shape) in self._slices.items()}
         ops.f16_split(self.flat.data, self._flat_hi, self._flat_lo)
@@ -254,8 +255,7 @@ class CSPNet(nn.Module):
         for i in range(self.num_layers):
             q = "l%d." % i
             if i not in self._pqr_hi:
-                self._pqr_hi[i] = torch.empty(3 * H, H, device=self.flat.device, dtype=torch.float16)
-                self._pqr_lo[i] = torch.empty(3 * H, H, device=self.flat.device, dtype=torch.float16)
+                self._pqr_hi[i], self._pqr_lo[i] = torch.empty(2, 3 * H, H, device=self.flat.device, dtype=torch.float16)
             for dst, src in ((self._pqr_hi[i], self._hi), (self._pqr_lo[i], self._lo)):
                 dst[:2 * H].copy_(src[q + "w_pq"])
                 dst[2 * H:].copy_(src[q + "wn1"][:, :H])

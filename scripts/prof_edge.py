@@ -1,6 +1,6 @@
 """Driver for ncu captures of the two per-edge GEMMs exactly as CSPNet issues them at the benchmark batch
 (256 crystals, 34 445 edges): one score-network evaluation to fill the workspace, then the two launches of layer 0
-a few times.   ncu --set full -k regex:tc_gemm_kernel ... python scripts/prof_edge.py"""
+a few times.   ncu --set full -k regex:edge_pair_kernel ... python scripts/prof_edge.py"""
 import os
 import sys
 
@@ -23,7 +23,9 @@ ws = dec.workspace(g, False)
 presplit, merged = dec.edge_mode(g.E)
 torch.cuda.synchronize()
 print("E =", g.E, "presplit", presplit, "merged", merged)
+H = dec.hidden_dim
 for rep in range(3):
+    ws.cat[0][:, H:].zero_()
     dec.edge_gemm1(0, ws, g, g.E, ws.a1[0], False, presplit, merged)
-    dec.edge_gemm2(0, ws, g.E, ws.a1[0], False, merged)
+    dec.edge_gemm2(0, ws, g, g.E, ws.a1[0], ws.cat[0][:, H:], False, merged)
 torch.cuda.synchronize()
