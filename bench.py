@@ -123,8 +123,8 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of edge_pair_kernel<0> at the default workload, from the committed
-# ncu --set full capture (profiles/r2_edge_pair_ncu_raw.csv); None until that capture exists
-PAIR_TRAFFIC = None
+# ncu --set full capture (profiles/r2_edge_pair_ncu_raw.csv)
+PAIR_TRAFFIC = 146.9e6      # 118.8 MB read + 28.1 MB written
 
 WORKLOAD = "DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU"
 
