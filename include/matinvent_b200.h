@@ -194,12 +194,11 @@ int mi_edge_fourier(const float* x, const int* edge_src, const int* edge_dst, co
  *   mean != 0: scale_s = 1 / max(count, 1) (torch_scatter.scatter(reduce='mean'), cspnet.py:79,281)
  *   mean == 0: plain sum.  accumulate != 0: out += result.
  * H must be a multiple of 4 and rows 16-byte aligned.  amax_out (nullable, [S]) receives max |out[s][:]|
- * (for the row rescaling of mi_tc_gemm).  This is the edge-scatter roofline kernel.
- * rows: ptr[S] (the total number of rows) when the caller knows it, else 0.  With perm == NULL and rows > 0 the
- * streaming kernel runs: every block owns the segments that start inside its 32-row chunk, so blocks move equal bytes
- * whatever the segment sizes (same summation order per segment, bit-identical results). */
+ * (for the row rescaling of mi_tc_gemm).  This is the edge-scatter roofline kernel (the inference path forms the
+ * scatter-mean of the second per-edge block in that GEMM's epilogue, mi_edge_block2; this kernel serves the knn graphs
+ * and every segment sum of the backward). */
 int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
-                      int S, int H, int mean, int accumulate, float* amax_out, int rows, mi_stream_t stream);
+                      int S, int H, int mean, int accumulate, float* amax_out, mi_stream_t stream);
 
 /* dX[e][:] = dOut[idx[e]][:] * (inv_count ? 1/max(cnt(idx[e]),1) : 1) * (z ? silu'(z[e][:]) : 1)
  * (backward of segment mean + SiLU).  idx nullable -> identity; ptr = CSR used for counts (nullable ->

@@ -42,7 +42,7 @@ PROTOTYPES = {
     "mi_edge_block2": [i, i, i, p, p, i, p, p, p, i, p, p, p, i, p, p, p, p],
     "mi_fc_edges": [p, p, i, i, i, p, p, p, p, p, p, p, p],
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, f, f, p],
-    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, i, p],
+    "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p, p],
     "mi_colsum": [p, i, i, i, p, i, p],
     "mi_layernorm_fwd": [p, i, p, p, p, i, p, p, i, i, f, p, p],

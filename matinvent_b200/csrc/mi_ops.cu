@@ -243,110 +243,6 @@ __global__ void __launch_bounds__(128) segment_reduce_kernel(const float* __rest
     }
 }
 
-// Streaming variant for segments that are runs of consecutive rows (perm == NULL): every block owns the segments that
-// START inside its chunk of `chunk` rows (it reads past the chunk's end to finish its last segment and skips the
-// segment that began before it), so all blocks move about the same number of bytes whatever the segment sizes —
-// the one-segment-per-block kernel above leaves a block with a 1-row segment idle while its neighbour sums 20 rows.
-// The first owned segment is found by a cooperative lower bound over ptr (two dependent loads for S <= 16k).
-// Same accumulation order per segment as segment_reduce_kernel (results are bit-identical).
-__device__ __forceinline__ int block_lower_bound(const int* __restrict__ ptr, int n, int key, int* sh) {
-    // first i in [0, n) with ptr[i] >= key, n if none; blockDim.x == 128; sh: 5 ints of shared memory
-    int lo = 0, hi = n;
-    const int t = threadIdx.x;
-    while (true) {
-        const int span = hi - lo;
-        const int step = span > 128 ? (span + 127) / 128 : 1;
-        const int idx = lo + t * step;
-        const bool pred = idx < hi && __ldg(ptr + idx) >= key;
-        const unsigned b = __ballot_sync(0xffffffffu, pred);
-        if ((t & 31) == 0) sh[t >> 5] = b ? (t + __ffs(b) - 1) : 1 << 30;
-        __syncthreads();
-        const int first = min(min(sh[0], sh[1]), min(sh[2], sh[3]));      // first sampled position with ptr >= key
-        __syncthreads();
-        if (step == 1) return first >= (1 << 30) ? hi : lo + first;
-        const int nhi = first >= (1 << 30) ? hi : min(hi, lo + first * step);
-        const int nlo = first >= (1 << 30) ? lo + ((span - 1) / step) * step + 1 : (first == 0 ? lo : lo + (first - 1) * step + 1);
-        lo = min(nlo, nhi);
-        hi = nhi;
-        if (lo >= hi) return hi;
-    }
-}
-
-__global__ void __launch_bounds__(128) segment_rows_kernel(const float* __restrict__ X, int ldx, const int* __restrict__ ptr,
-                                                           float* __restrict__ out, int ldo, int H4, int S, int chunk,
-                                                           int mean, int accumulate, float* __restrict__ amax_out) {
-    __shared__ int sh[5];
-    __shared__ float wm[4];
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
-    const bool live = c < H4;
-    const long long ld4 = ldx >> 2;
-    const float4* base = reinterpret_cast<const float4*>(X) + c;
-    const int E = __ldg(ptr + S);
-    const long long r0 = (long long)blockIdx.x * chunk;
-    // owned: segments s with r0 <= ptr[s] < r0 + chunk; the last block also owns the empty segments at ptr == E
-    const bool last_block = r0 + chunk >= E;
-    if (r0 >= E && !(blockIdx.x == 0)) return;
-    int s = block_lower_bound(ptr, S, (int)r0, sh);
-    int beg = s < S ? __ldg(ptr + s) : E;
-    while (s < S && (beg < r0 + chunk || last_block)) {
-        const int end = __ldg(ptr + s + 1);
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-            float4 a0 = r, a1 = r, a2 = r, a3 = r;
-            int k = beg;
-            for (; k + 8 <= end; k += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_stream(base + (long long)(k + u) * ld4);
-#pragma unroll
-                for (int u = 0; u < 8; u += 4) {
-                    a0.x += v[u].x; a0.y += v[u].y; a0.z += v[u].z; a0.w += v[u].w;
-                    a1.x += v[u + 1].x; a1.y += v[u + 1].y; a1.z += v[u + 1].z; a1.w += v[u + 1].w;
-                    a2.x += v[u + 2].x; a2.y += v[u + 2].y; a2.z += v[u + 2].z; a2.w += v[u + 2].w;
-                    a3.x += v[u + 3].x; a3.y += v[u + 3].y; a3.z += v[u + 3].z; a3.w += v[u + 3].w;
-                }
-            }
-            for (; k + 4 <= end; k += 4) {
-                float4 v0 = ld_stream(base + (long long)k * ld4), v1 = ld_stream(base + (long long)(k + 1) * ld4);
-                float4 v2 = ld_stream(base + (long long)(k + 2) * ld4), v3 = ld_stream(base + (long long)(k + 3) * ld4);
-                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-                a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-                a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-                a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
-            }
-            for (; k < end; ++k) {
-                float4 v0 = ld_stream(base + (long long)k * ld4);
-                a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-            }
-            r = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
-                            (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
-            if (mean) {
-                float cnt = (float)max(end - beg, 1);
-                r.x /= cnt; r.y /= cnt; r.z /= cnt; r.w /= cnt;
-            }
-            float4* o = reinterpret_cast<float4*>(out + (long long)s * ldo) + c;
-            if (accumulate) {
-                float4 t = *o;
-                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
-            }
-            *o = r;
-        }
-        if (amax_out) {
-            float mx = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w)));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = mx;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                mx = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
-                atomicMax(reinterpret_cast<unsigned*>(amax_out + s), __float_as_uint(mx));
-            }
-            __syncthreads();
-        }
-        ++s;
-        beg = end;
-    }
-}
 
 __global__ void gather_rows_dsilu_kernel(const float* __restrict__ dOut, int ldd, const int* __restrict__ idx,
                                          const int* __restrict__ ptr, const float* __restrict__ z, int ldz,
@@ -944,7 +840,7 @@ extern "C" int mi_edge_fourier(const float* x, const int* edge_src, const int* e
 }
 
 extern "C" int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, float* out, int ldo,
-                                 int S, int H, int mean, int accumulate, float* amax_out, int rows, mi_stream_t stream) {
+                                 int S, int H, int mean, int accumulate, float* amax_out, mi_stream_t stream) {
     MI_CHECK_ARG(S >= 0 && H > 0 && H % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "H, ldx, ldo must be multiples of 4");
     if (S == 0) return MI_OK;
     MI_CHECK_ARG(X && ptr && out && mi_host_aligned16(X) && mi_host_aligned16(out), "null or unaligned pointer");
@@ -956,14 +852,6 @@ extern "C" int mi_segment_reduce(const float* X, int ldx, const int* ptr, const 
         MI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int gy = mi_div_up(H4, 128);
-    if (!perm && rows > 0 && S >= 64) {
-        // runs of consecutive rows, total row count known: blocks own equal 32-row chunks (segment_rows_kernel)
-        const int chunk = 32;
-        dim3 grid_r((unsigned)mi_div_up(rows, chunk), gy);
-        segment_rows_kernel<<<grid_r, 128, 0, (cudaStream_t)stream>>>(X, ldx, ptr, out, ldo, H4, S, chunk, mean, accumulate, amax_out);
-        MI_CHECK_LAUNCH();
-        return MI_OK;
-    }
     int gx = sms * 16 / gy;                       // 16 resident 128-thread blocks per SM: one full wave, grid-stride
     if (gx > S) gx = S;
     if (gx < 1) gx = 1;

@@ -524,7 +524,7 @@ class CSPNet(nn.Module):
                         flags=ops.TC_MERGED, scatter=(agg, g.edge_src, g.edge_w, ws.amax_agg[i]), **epi2)
         else:
             self._linear(a1, q + "w2", ws.a2, E, **epi2)
-            ops.segment_reduce(ws.a2, g.seg_ptr, agg, N, H, mean=True, amax_out=ws.amax_agg[i], rows=E)
+            ops.segment_reduce(ws.a2, g.seg_ptr, agg, N, H, mean=True, amax_out=ws.amax_agg[i])
 
     # ------------------------------------------------------------------ forward
     def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None, reuse_embedding=False):
@@ -636,7 +636,7 @@ class CSPNet(nn.Module):
         if heads[1]:
             self._linear(hf, "coord_w", ws.pred_x, N)
         if heads[0]:
-            ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True, rows=N)
+            ops.segment_reduce(hf, g.node_off, ws.gmean, B, H, mean=True)
             if self.ip:
                 self._linear(ws.gmean, "lattice_w", ws.lat9, B)
                 ops.bmm3(ws.lat9, l, ws.pred_l, B)
@@ -746,10 +746,10 @@ class CSPNet(nn.Module):
             # a1 = silu(z1) ; z1 = Phi w_f^T + P[src] + Q[dst] + C[graph]
             self._dgrad(ws.dz2, q + "w2", ws.dz1, E, ws.amax_dz2[i], act=ACT_DSILU, z_in=ws.z1[i])
             self._wgrad(ws.dz1, ws.phi, q + "w_f", H, F6, E, ws=ws, xt=phi_t)
-            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i], rows=E)
+            ops.segment_reduce(ws.dz1, g.seg_ptr, ws.dpq[:, :H], N, H, mean=False, amax_out=ws.amax_dpq[i])
             ops.segment_reduce(ws.dz1, g.dst_ptr, ws.dpq[:, H:], N, H, perm=g.dst_perm, mean=False,
                                amax_out=ws.amax_dpq[i])
-            ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False, rows=N)
+            ops.segment_reduce(ws.dpq[:, :H], g.node_off, ws.dcb, B, H, mean=False)
             ops.colsum(ws.dcb, B, H, G[q + "b1"])
             self._wgrad(ws.dcb, ws.ips, q + "w_l", H, 9, B)
             self._wgrad(ws.dpq, cat[:, :H], q + "w_pq", 2 * H, H, N, ws=ws)
@@ -762,7 +762,7 @@ class CSPNet(nn.Module):
                 dh.add_(ws.dcat[:, :H])
         # ---- embedding
         self._wgrad(dh, ws.h0, "lat_w_h", H, H, N)
-        ops.segment_reduce(dh, g.node_off, ws.dtb, B, H, mean=False, rows=N)
+        ops.segment_reduce(dh, g.node_off, ws.dtb, B, H, mean=False)
         ops.colsum(ws.dtb, B, H, G["lat_b"])
         self._wgrad(ws.dtb, temb, "lat_w_t", H, T, B)
         ops.sgemm(dh, W["lat_w_h"], ws.dzn, transB=False, M=N, N=H, K=H)

@@ -201,11 +201,10 @@ def edge_fourier(x, edge_src, edge_dst, cell_off, E, F, frac_diff, phi, phi_hi=N
                                 ld, _p(phi_hi), _p(phi_lo), op_scale, lo_scale, _stream()), "mi_edge_fourier")
 
 
-def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None, rows=0):
-    """rows = ptr[S] when known on the host (selects the balanced streaming kernel for consecutive-row segments)"""
+def segment_reduce(X, ptr, out, S, H, perm=None, mean=True, accumulate=False, amax_out=None):
     _f32(X), _f32(out), _i32(ptr), _i32(perm), _f32(amax_out)
     check(lib().mi_segment_reduce(_p(X), _ld(X), _p(ptr), _p(perm), _p(out), _ld(out), S, H, int(mean),
-                                  int(accumulate), _p(amax_out), int(rows), _stream()), "mi_segment_reduce")
+                                  int(accumulate), _p(amax_out), _stream()), "mi_segment_reduce")
     return out
 
 

@@ -307,35 +307,3 @@ def test_philox_statistics_and_offsets(ops):
     assert float(u.min()) >= 0 and float(u.max()) < 1 and abs(float(u.mean()) - 0.5) < 2e-3
 
 
-@pytest.mark.parametrize("kind", ["fc", "with_empty", "long", "tiny"])
-def test_segment_reduce_streaming_kernel_bit_identical(ops, kind):
-    """the balanced streaming kernel (rows given, perm == NULL) against the one-segment-per-block kernel: bit-identical
-    sums / means / maxima, empty segments (leading, trailing, in the middle) written as zeros, accumulate mode"""
-    g = torch.Generator().manual_seed(5)
-    if kind == "fc":
-        ns = torch.randint(1, 21, (300,), generator=g).tolist()
-        sizes = [n for n in ns for _ in range(n)]
-    elif kind == "with_empty":
-        sizes = [0, 0] + torch.randint(0, 9, (500,), generator=g).tolist() + [0, 0, 0]
-    elif kind == "long":
-        sizes = torch.randint(1, 200, (90,), generator=g).tolist()
-    else:
-        sizes = [3] * 64
-    S, H = len(sizes), 512
-    E = sum(sizes)
-    ptr = torch.tensor([0] + torch.cumsum(torch.tensor(sizes), 0).tolist(), dtype=torch.int32).cuda()
-    X = torch.randn(max(E, 1), H, generator=g).cuda()
-    for mean in (True, False):
-        a, b = torch.full((S, H), 9.0, device="cuda"), torch.full((S, H), 9.0, device="cuda")
-        ma, mb = torch.zeros(S, device="cuda"), torch.zeros(S, device="cuda")
-        ops.segment_reduce(X, ptr, a, S, H, mean=mean, amax_out=ma)                    # one segment per block
-        ops.segment_reduce(X, ptr, b, S, H, mean=mean, amax_out=mb, rows=E)            # streaming
-        assert torch.equal(a, b) and torch.equal(ma, mb), (kind, mean)
-    ops.segment_reduce(X, ptr, a, S, H, mean=False, accumulate=True)
-    ops.segment_reduce(X, ptr, b, S, H, mean=False, accumulate=True, rows=E)
-    assert torch.equal(a, b)
-    idx = torch.repeat_interleave(torch.arange(S), torch.tensor(sizes)).cuda()
-    ref = torch.zeros(S, H, dtype=torch.float64, device="cuda").index_add_(0, idx, X[:E].double())
-    c = torch.empty(S, H, device="cuda")
-    ops.segment_reduce(X, ptr, c, S, H, mean=False, rows=E)
-    assert float((c.double() - ref).abs().max()) < 1e-4
