@@ -190,7 +190,9 @@ class CSPNet(nn.Module):
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
         # per-edge blocks on CTA pairs (csrc/mi_edge.cu): inference, merged tiles, LayerNorm'd node path
         self.use_pair = os.environ.get("MI_EDGE_PAIR", "1") != "0"
-        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
+        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"
+        self.overlap_fourier = os.environ.get("MI_OVERLAP_FOURIER", "1") != "0"
+        self._side = None      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
         self._bounds = None
@@ -544,16 +546,18 @@ class CSPNet(nn.Module):
         # embedding (cspnet.py:264-271):  h = [Lin_A(a) | temb_b] W^T + b
         ws.amax.zero_()
         reuse = reuse_embedding and not train
+        # (the Fourier basis is compute-bound — 26 M sincosf per evaluation fill every SM — so running it on a side stream
+        # next to the embedding GEMMs measured no gain: 98.4 vs 98.7 crystals/s)
+        presplit, merged = self.edge_mode(E)
+        ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
+                         ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
+                         op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
         if not reuse:
             # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
             ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
             self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
             self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
             ops.lattice_ip(l, ws.ips, B)
-        presplit, merged = self.edge_mode(E)
-        ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
-                         ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
-                         op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
         # per-crystal term C_b of the first edge linear, all layers in one launch (the layer blocks of the flat weight
         # buffer are equally spaced)
         if not reuse:

@@ -259,8 +259,14 @@ class _StepState:
         self.x, self.l, self.a = x, l, a
         self.x_half = torch.empty_like(x)
         self.temb = torch.empty(B, module.time_dim, device=dev)
-        self.zx_c, self.zx_p = torch.zeros(N, 3, device=dev), torch.zeros(N, 3, device=dev)
-        self.zl, self.za = torch.zeros(B, 3, 3, device=dev), torch.zeros(N, A, device=dev)
+        # the four noise draws of a step are views of ONE buffer: with in-graph Philox noise a step costs one fill
+        sizes = [N * 3, B * 9, N * A, N * 3]
+        offs = [0]
+        for n_ in sizes:
+            offs.append(offs[-1] + (n_ + 3) // 4 * 4)
+        self.znoise = torch.zeros(offs[-1], device=dev)
+        self.zx_c, self.zl = self.znoise[offs[0]:offs[0] + N * 3].view(N, 3), self.znoise[offs[1]:offs[1] + B * 9].view(B, 3, 3)
+        self.za, self.zx_p = self.znoise[offs[2]:offs[2] + N * A].view(N, A), self.znoise[offs[3]:offs[3] + N * 3].view(N, 3)
         self.ws = module.decoder.workspace(g, False)
         self.coef = co.table().to(dev)
         self.ttab = module.time_table()
@@ -287,8 +293,7 @@ class _StepState:
         dec = m.decoder
         ops.sampler_step_begin(self.t_dev, self.ttab, self.temb, B, m.time_dim)
         if with_noise and self.in_graph_noise:
-            for buf in (self.zx_c, self.zl, self.za, self.zx_p):
-                self.noise.fill(buf)
+            self.noise.fill(self.znoise)
         nz = (lambda t: t) if with_noise else (lambda t: None)
         # corrector: only the coordinate head is consumed (diffusion.py:327-330)
         _, px, _ = dec.forward_graph(g, self.temb, self.a, self.x, self.l, heads=(False, True, False), ws=ws)
