@@ -190,9 +190,7 @@ class CSPNet(nn.Module):
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
         # per-edge blocks on CTA pairs (csrc/mi_edge.cu): inference, merged tiles, LayerNorm'd node path
         self.use_pair = os.environ.get("MI_EDGE_PAIR", "1") != "0"
-        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"
-        self.overlap_fourier = os.environ.get("MI_OVERLAP_FOURIER", "1") != "0"
-        self._side = None      # fused node-level chain (inference, H = 512)
+        self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
         self._bounds = None
