@@ -198,6 +198,8 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
     cluster_sync_pair();                                          // the peer's barriers are initialised before anyone arrives on them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                   // the predecessor's output (A operand, P|Q rows) is complete
+    pdl_launch();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -387,7 +389,17 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
     const long long tiles = (long long)mi_div_up(p.M, 2 * TM) * (p.N / TNP);
     long long pairs = sms / 2;
     if (tiles < pairs) pairs = tiles;
-    edge_pair_kernel<MODE><<<(int)(2 * pairs), THREADS, C::SMEM_BYTES, s>>>(mAh, mAl, mWh, mWl, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = mi_pdl_enabled() ? 1 : 0;
+    MI_CUDA(cudaLaunchKernelEx(&cfg, edge_pair_kernel<MODE>, mAh, mAl, mWh, mWl, p));
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

@@ -161,6 +161,8 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                   // agg / amax of the preceding per-edge block are complete
+    pdl_launch();
     if (threadIdx.x == 0) NTRACE(1);
     const bool tr = threadIdx.x == EPI_WARP0 * 32;                 // the thread that stamps the epilogue side
     (void)tr;
@@ -614,7 +616,17 @@ extern "C" int mi_node_chain(int M, int Hdim, int n_phases, float* agg, int ld_a
     if ((rc = mi_tc_make_map_pair(&mX, xs_hi, xs_lo, M, H, H, R)) != MI_OK) return rc;
     if ((rc = mi_tc_make_map_pair(&mY, ys_hi, ys_lo, M, H, H, R)) != MI_OK) return rc;
     const int row_blocks = mi_div_up(M, R);
-    node_chain_kernel<<<row_blocks * CLUSTER, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mX, mY, mW0, mW1, mW2, p);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(row_blocks * CLUSTER));
+    lc.blockDim = dim3(THREADS);
+    lc.dynamicSmemBytes = SMEM_BYTES;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = la;
+    lc.numAttrs = mi_pdl_enabled() ? 1 : 0;
+    MI_CUDA(cudaLaunchKernelEx(&lc, node_chain_kernel, mX, mY, mW0, mW1, mW2, p));
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

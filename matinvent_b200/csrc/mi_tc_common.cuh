@@ -2,6 +2,7 @@
 // operand split, fast SiLU.  sm_100a only.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 
@@ -111,6 +112,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialisation attribute starts while its predecessor
+// still runs; pdl_wait() returns once the predecessor has completed and its writes are visible, pdl_launch() lets the
+// successor start.  Every kernel here does its set-up (barriers, TMEM, tensor-map prefetch) first, then waits, then
+// triggers: at most two kernels overlap, and nothing before the wait touches global memory the predecessor works on.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 16-column variants (rolled epilogue loops) and the store back to TMEM
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -134,6 +142,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 // host side (defined in mi_tc.cu): 2-D row-major [rows, cols] tensor map, box = [box_rows, 32 columns], zero OOB fill;
 // fp32 operands use 128-byte swizzle rows, fp16 operands 64-byte rows
 int mi_tc_get_encode();
+// launch attribute for programmatic dependent launch: OFF unless MI_PDL=1 — measured twice (round 1 on the single-CTA
+// kernels, round 2 on the CTA-pair / cluster kernels: 2 617 vs 2 636 us per reverse step at 256 crystals, 1 717 vs 1 710
+// at 128, inside the run-to-run spread): the graph replay already leaves ~1 us between kernels and a successor's CTAs
+// cannot become resident before the predecessor's leave (shared memory)
+inline bool mi_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MI_PDL");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on != 0;
+}
 int mi_tc_make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, bool half);
 // one 3-D map over an fp16 (hi, lo) operand pair (lo follows hi by a multiple of 16 bytes): box = [2, box_rows, 32 columns]
 int mi_tc_make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld, int box_rows);
