@@ -50,6 +50,7 @@ static_assert(SMEM_BYTES <= 232448, "does not fit the SM");
 static_assert((3 * S + 5) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 constexpr uint32_t ACC_COLS = 2 * TN, TMEM_COLS = 2 * ACC_COLS;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_WIDE = (1u << 4) | ((uint32_t)((2 * TN) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // N = [W_hi | W_lo]
 
 struct Params {
     int M, n_phases;
@@ -235,12 +236,16 @@ node_chain_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                         const uint32_t st = smem_u32(ring + s * OPB);
                         const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + (uint32_t)(p.rows * TK * 2));
                         const uint64_t d_whi = umma_desc(st + 2 * A_H), d_wlo = umma_desc(st + 2 * A_H + W_H);
+                        // W_hi and W_lo are adjacent tiles of the slot and the main / correction accumulators adjacent TMEM
+                        // columns: ONE 256-wide MMA forms a_hi.w_hi and a_hi.w_lo (A_hi is read from shared memory once
+                        // instead of twice: the 128-wide tiles of this kernel run at the shared-memory limit), a 128-wide one
+                        // adds a_lo.w_hi to the correction
+                        (void)d_wlo;
 #pragma unroll
                         for (int k = 0; k < TK / 16; ++k) {
                             const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                            umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, (uint32_t)((kb | k) != 0));
-                            umma_f16(acc + TN, d_ahi + adv, d_wlo + adv, IDESC, 1u);
+                            umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC_WIDE, (kb | k) != 0);
+                            umma_f16(acc + TN, d_alo + adv, d_whi + adv, IDESC, 1u);
                         }
                         umma_commit(&op_empty[s]);
                     }
