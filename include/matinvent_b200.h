@@ -207,6 +207,9 @@ int mi_segment_reduce(const float* X, int ldx, const int* ptr, const int* perm, 
 int mi_gather_rows_dsilu(const float* dOut, int ldd, const int* idx, const int* ptr, const float* z,
                          int ldz, float* dX, int ldx, int E, int H, float* amax_out, mi_stream_t stream);
 
+/* out[r] = max_c |X[r][c]|: row maxima of an operand whose producer does not report them (the atom-type state of the
+ * sampler before the embedding GEMM), for epi->a_amax */
+int mi_row_amax(const float* X, int ldx, int rows, int cols, float* out, mi_stream_t stream);
 /* out[n] (+)= sum_m X[m][n]  (bias gradients) */
 int mi_colsum(const float* X, int ldx, int M, int N, float* out, int accumulate, mi_stream_t stream);
 
@@ -236,6 +239,14 @@ int mi_lattice_ip(const float* L, float* ips, int B, mi_stream_t stream);
 int mi_lattice_linear(const float* L, const float* W, const float* bias, float* out, int ldo, int B, int H,
                       int n_sets, long long w_stride, long long bias_stride, long long out_stride,
                       mi_stream_t stream);
+/* The output heads of CSPNet at inference in one launch, one CTA per crystal (cspnet.py:276-294):
+ *   hf = LayerNorm(h; ln_g, ln_b) (ln_g == NULL: hf = h);  pred_x [N,3] = hf coord_w^T;  pred_a [N,A] = hf type_w^T + type_b;
+ *   pred_l [B,3,3] = lattice_w (mean over the crystal's atoms of hf), multiplied by L[b] from the right when ip != 0.
+ * Any of pred_x / pred_a / pred_l may be NULL (the corrector evaluation only needs pred_x).  FP32 CUDA-core arithmetic;
+ * replaces mi_layernorm_fwd + 3 GEMM launches + mi_segment_reduce + mi_bmm3.  H in {128, 256, 512, 1024}. */
+int mi_output_heads(const float* h, int ldh, const int* node_off, int B, int H, const float* ln_g, const float* ln_b, float eps,
+                    const float* coord_w, float* pred_x, const float* type_w, const float* type_b, int A, float* pred_a,
+                    const float* lattice_w, const float* L, int ip, float* pred_l, mi_stream_t stream);
 /* out[b] = A[b] (3x3) @ L[b] (3x3)   (cspnet.py:288-289); transL != 0 -> A[b] @ L[b]^T (its backward) */
 int mi_bmm3(const float* A, const float* L, float* out, int B, int transL, mi_stream_t stream);
 /* SinusoidalTimeEmbeddings (diffusion.py:53-66): out[b] = [sin(t_b f_k) || cos(t_b f_k)], dim even;

@@ -44,12 +44,14 @@ PROTOTYPES = {
     "mi_edge_fourier": [p, p, p, p, i, i, p, p, i, p, p, f, f, p],
     "mi_segment_reduce": [p, i, p, p, p, i, i, i, i, i, p, p],
     "mi_gather_rows_dsilu": [p, i, p, p, p, i, p, i, i, i, p, p],
+    "mi_row_amax": [p, i, i, i, p, p],
     "mi_colsum": [p, i, i, i, p, i, p],
     "mi_layernorm_fwd": [p, i, p, p, p, i, p, p, i, i, f, p, p],
     "mi_layernorm_fwd_split": [p, i, p, p, p, i, p, p, i, p, p, i, i, p, p, i, i, f, p],
     "mi_layernorm_bwd": [p, i, p, i, p, p, p, p, i, i, p, p, i, i, p],
     "mi_lattice_ip": [p, p, i, p],
     "mi_lattice_linear": [p, p, p, p, i, i, i, i, ll, ll, ll, p],
+    "mi_output_heads": [p, i, p, i, i, p, p, f, p, p, p, p, i, p, p, p, i, p, p],
     "mi_bmm3": [p, p, p, i, i, p],
     "mi_time_embed": [p, p, i, i, p, p],
     "mi_lattice_params_to_matrix": [p, p, p, i, p],

@@ -293,6 +293,137 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N
     }
 }
 
+// ------------------------------------------------------------------------------------ output heads (inference)
+// final LayerNorm + coord_out + type_out + graph mean + lattice_out (+ L product) of cspnet.py:276-294 in ONE launch, one
+// CTA per crystal.  As separate launches these were 3 (corrector) / 7 (predictor) latency-bound kernels of ~15 us each for
+// 0.3 GFLOP; here the crystal's rows are normalised into shared memory once (same arithmetic as layernorm_fwd_kernel) and
+// every warp takes output columns: the weight row sits in registers, the rows come from shared memory.
+constexpr int HEAD_ROWS = 32;                       // rows per pass through shared memory
+template <int NV>                                   // H = 32 * NV
+__global__ void __launch_bounds__(256, 2) output_heads_kernel(const float* __restrict__ h, int ldh, const int* __restrict__ node_off,
+                                                              const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                              float eps, const float* __restrict__ coord_w, float* __restrict__ pred_x,
+                                                              const float* __restrict__ type_w, const float* __restrict__ type_b, int A,
+                                                              float* __restrict__ pred_a, const float* __restrict__ lattice_w,
+                                                              const float* __restrict__ L, int ip, float* __restrict__ pred_l) {
+    constexpr int H = 32 * NV;
+    extern __shared__ float hs[];                    // [HEAD_ROWS][H] normalised rows | [H] column sums | [9]
+    float* colsum = hs + HEAD_ROWS * H;
+    float* lat9 = colsum + H;
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int r0 = __ldg(node_off + b), r1 = __ldg(node_off + b + 1);
+    for (int c = threadIdx.x; c < H; c += blockDim.x) colsum[c] = 0.f;
+    const int n_out = (pred_x ? 3 : 0) + (pred_a ? A : 0);
+    for (int c0 = r0; c0 < r1; c0 += HEAD_ROWS) {
+        const int nrow = min(HEAD_ROWS, r1 - c0);
+        __syncthreads();
+        for (int r = warp; r < HEAD_ROWS; r += nw) {  // LayerNorm (or a plain copy) of one row per warp; rows past the crystal: zeros
+            float xv[NV];
+            if (r < nrow) {
+                const float* xr = h + (long long)(c0 + r) * ldh;
+                float sm = 0.f;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) { xv[i] = xr[lane + 32 * i]; sm += xv[i]; }
+                if (ln_g) {
+                    sm = mi_warp_sum(sm);
+                    const float mean = sm / (float)H;
+                    float v = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) { const float d = xv[i] - mean; v += d * d; }
+                    v = mi_warp_sum(v);
+                    const float rstd = 1.0f / sqrtf(v / (float)H + eps);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) xv[i] = (xv[i] - mean) * rstd * __ldg(ln_g + lane + 32 * i) + __ldg(ln_b + lane + 32 * i);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) xv[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) hs[r * H + lane + 32 * i] = xv[i];
+        }
+        __syncthreads();
+        if (pred_l)
+            for (int c = threadIdx.x; c < H; c += blockDim.x) {
+                float a = colsum[c];
+                for (int r = 0; r < nrow; ++r) a += hs[r * H + c];
+                colsum[c] = a;
+            }
+        const int nrow4 = (nrow + 3) & ~3;
+        for (int o = warp; o < n_out; o += nw) {      // one output column per warp: weight row in registers
+            const bool is_x = pred_x && o < 3;
+            const int oc = is_x ? o : o - (pred_x ? 3 : 0);
+            const float* wr = is_x ? coord_w + (long long)oc * H : type_w + (long long)oc * H;
+            float wv[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) wv[i] = __ldg(wr + lane + 32 * i);
+            const float bias = (!is_x && type_b) ? __ldg(type_b + oc) : 0.f;
+            for (int r = 0; r < nrow4; r += 4) {      // four rows at a time: independent FMA chains, one shared reduction
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                const float* hr = hs + r * H + lane;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    d0 = fmaf(hr[32 * i], wv[i], d0);
+                    d1 = fmaf(hr[H + 32 * i], wv[i], d1);
+                    d2 = fmaf(hr[2 * H + 32 * i], wv[i], d2);
+                    d3 = fmaf(hr[3 * H + 32 * i], wv[i], d3);
+                }
+                // reduce-scatter over the lanes: after two exchange steps every lane holds one of the four sums' halves
+                const bool up16 = lane & 16, up8 = lane & 8;
+                float s0 = up16 ? d2 : d0, s1 = up16 ? d3 : d1;               // keep rows {0,1} in the lower half, {2,3} in the upper
+                float t0 = up16 ? d0 : d2, t1 = up16 ? d1 : d3;
+                s0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+                s1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                float u = up8 ? s1 : s0, w_ = up8 ? s0 : s1;
+                u += __shfl_xor_sync(0xffffffffu, w_, 8);
+                u += __shfl_xor_sync(0xffffffffu, u, 4);
+                u += __shfl_xor_sync(0xffffffffu, u, 2);
+                u += __shfl_xor_sync(0xffffffffu, u, 1);
+                // lanes 0 / 8 / 16 / 24 hold rows r + 0 / 1 / 2 / 3
+                const int rr = r + ((lane >> 4) << 1) + ((lane >> 3) & 1);
+                if ((lane & 7) == 0 && rr < nrow) {
+                    if (is_x) pred_x[(long long)(c0 + rr) * 3 + oc] = u;
+                    else pred_a[(long long)(c0 + rr) * A + oc] = u + bias;
+                }
+            }
+        }
+    }
+    if (pred_l) {
+        __syncthreads();
+        const float inv = 1.0f / (float)max(r1 - r0, 1);
+        for (int o = warp; o < 9; o += nw) {
+            float d = 0.f;
+            for (int c = lane; c < H; c += 32) d = fmaf(colsum[c] * inv, __ldg(lattice_w + (long long)o * H + c), d);
+            d = mi_warp_sum(d);
+            if (lane == 0) lat9[o] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x < 9) {
+            const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+            float v = lat9[threadIdx.x];
+            if (ip) {                                 // pred_l = lattice_out(mean) (3x3) @ L[b]   (cspnet.py:288-289)
+                const float* l = L + 9 * (long long)b;
+                v = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v += lat9[3 * r + k] * __ldg(l + 3 * k + c);
+            }
+            pred_l[9 * (long long)b + threadIdx.x] = v;
+        }
+    }
+}
+
+// out[r] = max_c |X[r][c]|  (one warp per row): row maxima of an operand whose producer does not report them
+__global__ void row_amax_kernel(const float* __restrict__ X, int ldx, int rows, int cols, float* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = X + (long long)row * ldx;
+    float mx = 0.f;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, fabsf(xr[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) out[row] = mx;
+}
+
 // ------------------------------------------------------------------------------------ LayerNorm
 // one warp per row
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
@@ -941,6 +1072,48 @@ extern "C" int mi_lattice_linear(const float* L, const float* W, const float* bi
     if (B <= 0 || n_sets <= 0) return MI_OK;
     MI_CHECK_ARG(L && W && out && H > 0 && ldo >= H, "bad arguments");
     lattice_linear_kernel<<<dim3(B, n_sets), 128, 0, (cudaStream_t)stream>>>(L, W, bias, out, ldo, H, w_stride, bias_stride, out_stride);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
+template <int NV>
+static int launch_heads(const float* h, int ldh, const int* node_off, int B, const float* ln_g, const float* ln_b, float eps,
+                        const float* coord_w, float* pred_x, const float* type_w, const float* type_b, int A, float* pred_a,
+                        const float* lattice_w, const float* L, int ip, float* pred_l, cudaStream_t s) {
+    constexpr int H = 32 * NV;
+    const size_t smem = ((size_t)HEAD_ROWS * H + H + 16) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        MI_CUDA(cudaFuncSetAttribute(output_heads_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    output_heads_kernel<NV><<<B, 256, smem, s>>>(h, ldh, node_off, ln_g, ln_b, eps, coord_w, pred_x, type_w, type_b, A, pred_a,
+                                                 lattice_w, L, ip, pred_l);
+    MI_CHECK_LAUNCH();
+    return MI_OK;
+}
+
+extern "C" int mi_output_heads(const float* h, int ldh, const int* node_off, int B, int H, const float* ln_g, const float* ln_b,
+                               float eps, const float* coord_w, float* pred_x, const float* type_w, const float* type_b, int A,
+                               float* pred_a, const float* lattice_w, const float* L, int ip, float* pred_l, mi_stream_t stream) {
+    if (B <= 0) return MI_OK;
+    MI_CHECK_ARG(h && node_off && (H == 128 || H == 256 || H == 512 || H == 1024) && ldh >= H, "bad arguments (H in {128, 256, 512, 1024})");
+    MI_CHECK_ARG((ln_g == nullptr) == (ln_b == nullptr), "ln_g and ln_b go together");
+    MI_CHECK_ARG((!pred_x || coord_w) && (!pred_a || (type_w && A > 0)) && (!pred_l || (lattice_w && (!ip || L))), "null weight");
+    cudaStream_t s = (cudaStream_t)stream;
+#define MI_HEADS(NV) launch_heads<NV>(h, ldh, node_off, B, ln_g, ln_b, eps, coord_w, pred_x, type_w, type_b, A, pred_a, lattice_w, L, ip, pred_l, s)
+    switch (H) {
+        case 128: return MI_HEADS(4);
+        case 256: return MI_HEADS(8);
+        case 512: return MI_HEADS(16);
+        default: return MI_HEADS(32);
+    }
+#undef MI_HEADS
+}
+
+extern "C" int mi_row_amax(const float* X, int ldx, int rows, int cols, float* out, mi_stream_t stream) {
+    if (rows <= 0) return MI_OK;
+    MI_CHECK_ARG(X && out && cols > 0 && ldx >= cols, "bad arguments");
+    row_amax_kernel<<<mi_div_up(rows, 8), 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, cols, out);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }

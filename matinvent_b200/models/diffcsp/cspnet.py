@@ -190,10 +190,13 @@ class CSPNet(nn.Module):
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
         # per-edge blocks on CTA pairs (csrc/mi_edge.cu): inference, merged tiles, LayerNorm'd node path
         self.use_pair = os.environ.get("MI_EDGE_PAIR", "1") != "0"
+        self.compose_embedding = os.environ.get("MI_COMPOSE_EMB", "1") != "0"     # composed embedding GEMM (inference)
+        self.fused_heads = os.environ.get("MI_FUSED_HEADS", "1") != "0"    # one-launch output heads (inference)
         self.use_chain = os.environ.get("MI_NODE_CHAIN", "1") != "0"      # fused node-level chain (inference, H = 512)
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
         self._bounds = None
+        self._emb_hl = self._emb_bias = None
         # transposed copies W^T (fp16 head / tail) of the weights whose input gradients run on the tensor cores
         # (dX = dY W is the forward kernel with W^T as its weight); built once a backward has asked for them
         self._hiT, self._loT, self._wT = {}, {}, {}
@@ -219,6 +222,7 @@ class CSPNet(nn.Module):
         self._mhi, self._mlo, self._minv = {}, {}, {}
         self._pqr_hi, self._pqr_lo = {}, {}
         self._bounds = None
+        self._emb_hl = self._emb_bias = None
         self._hiT, self._loT, self._wT = {}, {}, {}
         self._tc_version = None
         return r
@@ -259,6 +263,17 @@ class CSPNet(nn.Module):
             for dst, src in ((self._pqr_hi[i], self._hi), (self._pqr_lo[i], self._lo)):
                 dst[:2 * H].copy_(src[q + "w_pq"])
                 dst[2 * H:].copy_(src[q + "wn1"][:, :H])
+        # inference: node_embedding and the h part of atom_latent_emb are two linear maps in a row (cspnet.py:264-271), composed
+        # once per weight update:  h = a (W_h E)^T + [temb W_t^T + b_l + W_h b_e][crystal]   (one K = A GEMM instead of two)
+        A8 = _pad8(self.max_atoms)
+        if self._emb_hl is None:
+            self._emb_hl = torch.zeros(2, H, A8, device=self.flat.device, dtype=torch.float16)
+            self._emb_bias = torch.empty(H, device=self.flat.device, dtype=torch.float32)
+        wh, E_ = self._views["lat_w_h"].double(), self._views["emb_w"].double()
+        wae = torch.zeros(H, A8, device=self.flat.device, dtype=torch.float32)
+        wae[:, :self.max_atoms] = (wh @ E_).float()
+        ops.f16_split(wae, self._emb_hl[0], self._emb_hl[1])
+        self._emb_bias.copy_((self._views["lat_b"].double() + wh @ self._views["emb_b"].double()).float())
         # a-priori bounds of the node chain's row scales (mi_node_chain), rounded up: {max_j ||W_b[j]||_1, max |b_n1|,
         # sqrt(H) max |gamma| + max |beta| of the NEXT layer's LayerNorm}
         if self._bounds is None:
@@ -550,7 +565,16 @@ class CSPNet(nn.Module):
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
                          ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
                          op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
-        if not reuse:
+        composed = (not train and self.use_tc and self.compose_embedding and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0)
+        if not reuse and composed:
+            # inference: the two embedding linears as one tensor-core GEMM over the composed weight (see _refresh_tc); the
+            # atom-type state has no producer that reports row maxima: one tiny kernel takes them
+            ops.row_amax(a, N, self.max_atoms, ws.amax_h0)
+            self._linear(temb, "lat_w_t", ws.tb, B, bias=self._emb_bias)
+            ops.tc_gemm(a, self._emb_hl[0], self._emb_hl[1], ws.h[0], M=N, N=H, K=self.max_atoms,
+                        gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
+            ops.lattice_ip(l, ws.ips, B)
+        elif not reuse:
             # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
             ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
             self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
@@ -627,6 +651,13 @@ class CSPNet(nn.Module):
                              a_amax=ws.amax_agg[i], amax_out=ws.amax_an1[i])
             self._linear(an1, q + "wn2", h_out, N, bias=W[q + "bn2"], z_out=ws.zn2[i] if train else None,
                          act=ACT_SILU, resid=h_in, a_amax=ws.amax_an1[i])
+        hL = ws.h[L]
+        if not train and self.fused_heads and H in (128, 256, 512, 1024):
+            # inference: final LayerNorm + the three heads in one launch, one CTA per crystal (cspnet.py:276-294)
+            ops.output_heads(hL, g.node_off, B, H, W["fin_g"] if self.ln else None, W["fin_b"] if self.ln else None,
+                             W["coord_w"], ws.pred_x if heads[1] else None, W["type_w"], W["type_b"],
+                             ws.pred_a if heads[2] else None, W["lattice_w"], l, self.ip, ws.pred_l if heads[0] else None)
+            return ws.pred_l, ws.pred_x, ws.pred_a
         hL = ws.h[L]
         if self.ln:
             ops.layernorm_fwd(hL, W["fin_g"], W["fin_b"], ws.hf, N, H,

@@ -215,6 +215,12 @@ def gather_rows_dsilu(dOut, idx, ptr, z, dX, E, H, amax_out=None):
     return dX
 
 
+def row_amax(X, rows, cols, out):
+    _f32(X), _f32(out)
+    check(lib().mi_row_amax(_p(X), _ld(X), rows, cols, _p(out), _stream()), "mi_row_amax")
+    return out
+
+
 def colsum(X, M, N, out, accumulate=True):
     _f32(X), _f32(out)
     check(lib().mi_colsum(_p(X), _ld(X), M, N, _p(out), int(accumulate), _stream()), "mi_colsum")
@@ -446,6 +452,17 @@ def edge_block2(E, a_hi, a_lo, a_bound, w_hi, w_lo, col_scale, bias, scat_out, s
     check(lib().mi_edge_block2(E, N, K, _p(a_hi), _p(a_lo), _ld(a_hi), _p(a_bound), _p(w_hi), _p(w_lo), _ld(w_hi), _p(col_scale),
                                _p(bias), _p(scat_out), _ld(scat_out), _p(scat_idx), _p(scat_w), _p(scat_amax), _stream()),
           "mi_edge_block2")
+
+
+def output_heads(h, node_off, B, H, ln_g, ln_b, coord_w, pred_x, type_w, type_b, pred_a, lattice_w, L, ip, pred_l, eps=1e-5):
+    """final LayerNorm + coordinate / type / lattice heads in one launch (any output may be None).  See mi_output_heads."""
+    for t in (h, ln_g, ln_b, coord_w, pred_x, type_w, type_b, pred_a, lattice_w, L, pred_l):
+        _f32(t)
+    _i32(node_off)
+    A = pred_a.shape[1] if pred_a is not None else 0
+    check(lib().mi_output_heads(_p(h), _ld(h), _p(node_off), B, H, _p(ln_g), _p(ln_b), float(eps), _p(coord_w), _p(pred_x),
+                                _p(type_w), _p(type_b), A, _p(pred_a), _p(lattice_w), _p(L), int(bool(ip)), _p(pred_l), _stream()),
+          "mi_output_heads")
 
 
 def weighted_field_sum(fields, weights, out):

@@ -307,3 +307,34 @@ def test_philox_statistics_and_offsets(ops):
     assert float(u.min()) >= 0 and float(u.max()) < 1 and abs(float(u.mean()) - 0.5) < 2e-3
 
 
+
+
+def test_output_heads_fused_kernel(ops):
+    """mi_output_heads (final LayerNorm + coordinate / type / lattice heads, one CTA per crystal) against float64 of
+    cspnet.py:276-294: crystals of 1..20 atoms and one longer than a shared-memory pass, with and without LayerNorm,
+    with and without the lattice product, partial head sets"""
+    g = torch.Generator().manual_seed(12)
+    ns = torch.randint(1, 21, (37,), generator=g).tolist() + [70, 1]
+    off = torch.tensor([0] + torch.cumsum(torch.tensor(ns), 0).tolist(), dtype=torch.int32).cuda()
+    N, B, H, A = sum(ns), len(ns), 512, 100
+    h = (_rand(N, H, seed=30) * torch.exp(_rand(N, 1, seed=31))).contiguous()
+    gam, bet = 1 + 0.2 * _rand(H, seed=32), 0.1 * _rand(H, seed=33)
+    cw, tw, tb, lw = _rand(3, H, seed=34) / 20, _rand(A, H, seed=35) / 20, _rand(A, seed=36), _rand(9, H, seed=37) / 20
+    L = _rand(B, 3, 3, seed=38)
+    seg = torch.repeat_interleave(torch.arange(B), torch.tensor(ns)).cuda()
+    for ln in (True, False):
+        for ip in (True, False):
+            hf = torch.nn.functional.layer_norm(h.double(), (H,), gam.double(), bet.double(), 1e-5) if ln else h.double()
+            rx, ra = hf @ cw.double().t(), hf @ tw.double().t() + tb.double()
+            gm = torch.zeros(B, H, dtype=torch.float64, device="cuda").index_add_(0, seg, hf) / torch.tensor(ns, device="cuda").double()[:, None]
+            rl = (gm @ lw.double().t()).view(B, 3, 3)
+            if ip:
+                rl = rl @ L.double()
+            px, pa, pl = torch.full((N, 3), 7.0, device="cuda"), torch.full((N, A), 7.0, device="cuda"), torch.full((B, 3, 3), 7.0, device="cuda")
+            ops.output_heads(h, off, B, H, gam if ln else None, bet if ln else None, cw, px, tw, tb, pa, lw, L, ip, pl)
+            assert rel_err(px, rx) < 2e-6 and rel_err(pa, ra) < 2e-6 and rel_err(pl, rl) < 2e-6, (ln, ip)
+    # coordinate head alone (the corrector evaluation): the other outputs are not touched
+    px2 = torch.empty(N, 3, device="cuda")
+    ops.output_heads(h, off, B, H, gam, bet, cw, px2, tw, tb, None, lw, L, True, None)
+    hf = torch.nn.functional.layer_norm(h.double(), (H,), gam.double(), bet.double(), 1e-5)
+    assert rel_err(px2, hf @ cw.double().t()) < 2e-6
