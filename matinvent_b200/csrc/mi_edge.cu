@@ -45,7 +45,8 @@ constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(TNP >> 3) << 17) | ((uint32_
 template <int MODE>
 struct ECfg {
     static constexpr int S = MODE == 0 ? 6 : 5;                                   // ring depth
-    static constexpr int EBUF_BYTES = MODE == 0 ? 0 : EPI_WARPS * 32 * EP * 4;   // block 2: per-warp transpose buffers
+    // block 2: per-warp transpose buffers; block 1: per-warp staging of a 32 x 32 (hi, lo) fp16 output chunk for TMA stores
+    static constexpr int EBUF_BYTES = MODE == 0 ? EPI_WARPS * 4096 : EPI_WARPS * 32 * EP * 4;
     static constexpr int RING_BYTES = S * OPB;
     static constexpr int SMEM_BYTES = RING_BYTES + EBUF_BYTES + BAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "does not fit the SM");
@@ -63,6 +64,16 @@ struct EdgeParams {
     const float* a_bound; const float* bias;
     float* scat_out; int scat_ld; const int* scat_idx; const float* scat_w; float* scat_amax;
 };
+
+#ifdef MI_EDGE_TRACE
+// Developer instrumentation (scripts/trace_edge.py builds a separate library with -DMI_EDGE_TRACE; never in the product
+// build): per-CTA, per-tile SM clock stamps of the pipeline roles.
+constexpr int ET_TILES = 6, ET_SLOTS = 8;
+__device__ long long g_etrace[160 * ET_TILES * ET_SLOTS];
+#define ETRACE(tl, slot) do { if ((tl) < ET_TILES) g_etrace[(blockIdx.x * ET_TILES + (tl)) * ET_SLOTS + (slot)] = clock64(); } while (0)
+#else
+#define ETRACE(tl, slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -97,6 +108,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
+// TMA store of a [32 rows x 32 columns] fp16 tile (SWIZZLE_64B in shared memory); rows / columns past the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_pair() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -110,11 +126,6 @@ __device__ __forceinline__ void ldnc8(const float* p, float* v) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
-__device__ __forceinline__ void st8(void* p, const uint32_t* u) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
-                 "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]) : "memory");
-}
-
 // Segment sums of one 32x32 chunk held in a warp's transpose buffer (row-major, pitch EP): lane = column, the rows of
 // every segment are walked in order and one 128-byte reduction per (segment, chunk) goes to the zeroed destination
 // (the same routine as mi_tc.cu's: a segment meets at most two 32-row windows, so the sum does not depend on order).
@@ -143,7 +154,8 @@ __device__ __forceinline__ void scatter_chunk(const float* ebuf, uint32_t starts
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-                 const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl, const EdgeParams p) {
+                 const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+                 const __grid_constant__ CUtensorMap mapOh, const __grid_constant__ CUtensorMap mapOl, const EdgeParams p) {
     using C = ECfg<MODE>;
     constexpr int S = C::S;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -188,6 +200,10 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAl) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapWl) : "memory");
+        if (MODE == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOh) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOl) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
@@ -210,6 +226,8 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                 tile_origin(tl, m0, n0);
                 const int s = (int)(it % (uint32_t)S);
                 mbar_wait(&empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+                if (kb == 0) ETRACE(tl, 0);
+                if (kb == nkb - 1) ETRACE(tl, 1);
                 uint8_t* st = ring + s * OPB;
                 const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
                 mbar_expect_tx_cluster(fb, OPB);
@@ -227,11 +245,14 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const uint32_t ab = (uint32_t)tl & 1;
                 const uint32_t acc = tmem_base + ab * ACC_COLS;
+                ETRACE(tl, 2);
                 mbar_wait(&acc_empty[ab], (((uint32_t)tl >> 1) & 1) ^ 1);
+                ETRACE(tl, 3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = (int)(it % (uint32_t)S);
                     mbar_wait(&full[s], (it / (uint32_t)S) & 1);
+                    if (kb == 0) ETRACE(tl, 4);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(ring + s * OPB);
                     const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + T_H);
@@ -246,6 +267,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                     umma_commit_pair(&empty[s]);
                 }
                 umma_commit_pair(&acc_full[ab]);
+                ETRACE(tl, 5);
             }
         }
     } else {
@@ -277,6 +299,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                 const float* prow = p.P + (long long)i1 * p.ld_pq;
                 const float* qrow = p.Q + (long long)i2 * p.ld_pq;
                 mbar_wait(&acc_full[ab], ((uint32_t)tl >> 1) & 1);
+                if (threadIdx.x == 64) ETRACE(tl, 6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
@@ -306,12 +329,28 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                         split2<1>(a[0], a[1], hi[j / 2], lo[j / 2]);
                         split2<1>(a[2], a[3], hi[j / 2 + 1], lo[j / 2 + 1]);
                     }
-                    if (ok) {
-                        const long long o = (long long)mrow * p.ld_out + n;
-                        st8(p.out_hi + o, hi); st8(p.out_hi + o + 16, hi + 8);
-                        st8(p.out_lo + o, lo); st8(p.out_lo + o + 16, lo + 8);
+                    // The chunk leaves through TMA: a row-per-lane global store costs one L1 wavefront per lane and instruction
+                    // (128 per chunk, a third of this epilogue's L1 time, and the epilogue paces this kernel:
+                    // scripts/trace_edge.py); 16-byte swizzled shared-memory stores cost 4.
+                    uint8_t* sh = reinterpret_cast<uint8_t*>(ebuf_all) + (warp - EPI_WARP0) * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);      // SWIZZLE_64B: 16-byte chunk ^ (row / 2) % 4
+                        *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(sh + 2048 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int r0_ = m0 + (int)rank * TM + q * 32;
+                        tma_store_2d(&mapOh, sh, n, r0_);
+                        tma_store_2d(&mapOl, sh + 2048, n, r0_);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
+                if (tl == my_tiles - 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             } else {
                 const float rowsc = p.alpha * pow2f(exp8(ok ? __ldg(p.a_bound + mrow) : 0.f));
                 int my_seg = -1;
@@ -326,6 +365,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                 const uint32_t seg_starts = __ballot_sync(0xffffffffu, lane == 0 || my_seg != prev);
                 float seg_rmax = 0.f;
                 mbar_wait(&acc_full[ab], ((uint32_t)tl >> 1) & 1);
+                if (threadIdx.x == 64) ETRACE(tl, 6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 tmem_ld32(tbase, v);
 #pragma unroll 1
@@ -353,6 +393,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                 }
                 if (p.scat_amax && my_seg >= 0) atomicMax(reinterpret_cast<unsigned*>(p.scat_amax + my_seg), __float_as_uint(seg_rmax));
             }
+            if (threadIdx.x == 64) ETRACE(tl, 7);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -375,6 +416,11 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
     if ((rc = mi_tc_make_map(&mAl, A_lo, p.M, p.K, lda, TM, true)) != MI_OK) return rc;
     if ((rc = mi_tc_make_map(&mWh, W_hi, p.N, p.K, ldw, TNP / 2, true)) != MI_OK) return rc;
     if ((rc = mi_tc_make_map(&mWl, W_lo, p.N, p.K, ldw, TNP / 2, true)) != MI_OK) return rc;
+    CUtensorMap mOh = mAh, mOl = mAl;                             // block 2 has no tensor output
+    if (MODE == 0) {
+        if ((rc = mi_tc_make_map(&mOh, p.out_hi, p.M, p.N, p.ld_out, 32, true)) != MI_OK) return rc;
+        if ((rc = mi_tc_make_map(&mOl, p.out_lo, p.M, p.N, p.ld_out, 32, true)) != MI_OK) return rc;
+    }
     static bool attr = false;
     if (!attr) {
         MI_CUDA(cudaFuncSetAttribute(edge_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -399,7 +445,7 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = mi_pdl_enabled() ? 1 : 0;
-    MI_CUDA(cudaLaunchKernelEx(&cfg, edge_pair_kernel<MODE>, mAh, mAl, mWh, mWl, p));
+    MI_CUDA(cudaLaunchKernelEx(&cfg, edge_pair_kernel<MODE>, mAh, mAl, mWh, mWl, mOh, mOl, p));
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
@@ -407,6 +453,13 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
 bool al32(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; }
 
 }  // namespace
+
+#ifdef MI_EDGE_TRACE
+extern "C" int mi_edge_trace_read(long long* out, int n) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_etrace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 extern "C" int mi_edge_block1(int E, int N, int K, const void* phi_hi, const void* phi_lo, int ld_phi, const void* w_hi,
                               const void* w_lo, int ld_w, const float* col_scale, float alpha, const float* P, const float* Q,
