@@ -188,6 +188,7 @@ class CSPNet(nn.Module):
         # merged-format copies (per-row scaled, single-accumulator 128x256 tiles) of the per-edge weights: used when
         # the edge count fills the machine with 256-wide tiles (see forward_graph)
         self.use_merged = os.environ.get("MI_TC_MERGED", "1") != "0"
+        self.force_merged = False      # merged tiles / CTA-pair kernels at any edge count (small parity runs on the benchmark's kernels)
         # per-edge blocks on CTA pairs (csrc/mi_edge.cu): inference, merged tiles, LayerNorm'd node path
         self.use_pair = os.environ.get("MI_EDGE_PAIR", "1") != "0"
         self.compose_embedding = os.environ.get("MI_COMPOSE_EMB", "1") != "0"     # composed embedding GEMM (inference)
@@ -495,7 +496,7 @@ class CSPNet(nn.Module):
         H, F = self.hidden_dim, self.num_freqs
         presplit = self.use_tc and (6 * F) % 8 == 0
         # MI_TC_FORCE_MERGED=1: merged tiles at any edge count (parity runs of small goldens on the benchmark's format)
-        fill = os.environ.get("MI_TC_FORCE_MERGED", "0") == "1" or ((E + 127) // 128) * (H // 256) >= ops.sm_count()
+        fill = self.force_merged or os.environ.get("MI_TC_FORCE_MERGED", "0") == "1" or ((E + 127) // 128) * (H // 256) >= ops.sm_count()
         merged = presplit and self.use_merged and H % 256 == 0 and fill
         return presplit, merged
 
