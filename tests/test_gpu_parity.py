@@ -530,3 +530,29 @@ def test_sample_degenerate_batches_vs_oracle(gold_small, num_atoms):
     assert wrapped_err(out["frac_coords"], ref["frac_coords"]) < 1e-4
     assert rel_err(out["lattices"], ref["lattices"]) < 1e-4
     assert torch.equal(_types(out["atom_types"]), _types(ref["atom_types"]))
+
+
+@pytest.mark.parametrize("style", ["knn", "fc"])
+def test_forward_benchmark_kernels_small_batches_vs_oracle(style):
+    """hidden 512 / 128 frequencies with the CTA-pair per-edge kernels and the cluster node chain forced at small edge
+    counts (decoder.force_merged), fully-connected AND periodic k-nearest-neighbour graphs (arbitrary dst rows in the
+    gathers, variable-length source segments in the fused scatter-mean), against the oracle"""
+    from oracle import diffcsp_oracle as O
+    hp = O.default_hparams(num_layers=2, edge_style=style, cutoff=6.0, max_neighbors=12, timesteps=10)
+    sd = O.init_params(hp, seed=3)
+    m = build_module(hp, sd, None)
+    m.decoder.force_merged = True
+    na = torch.tensor([5, 17, 1, 20, 9, 12, 3])
+    B, N = len(na), int(na.sum())
+    g = torch.Generator().manual_seed(4)
+    t = torch.randn(B, 256, generator=g)
+    a = torch.randn(N, 100, generator=g)
+    x = torch.rand(N, 3, generator=g)
+    l = 0.3 * torch.randn(B, 3, 3, generator=g) + 5.0 * torch.eye(3)
+    n2g = torch.repeat_interleave(torch.arange(B), na)
+    with torch.no_grad():
+        out = m.decoder(t.cuda(), a.cuda(), x.cuda(), l.cuda(), na, n2g)
+        ref = O.cspnet_forward(sd, hp, t, a, x, l, na, n2g)
+    errs = [rel_err(u, r) for u, r in zip(out, ref)]
+    print("benchmark kernels, %s graph, %d atoms: %s" % (style, N, " ".join("%.2e" % e for e in errs)))
+    assert max(errs) < 2e-5, errs
