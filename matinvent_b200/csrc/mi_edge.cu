@@ -35,7 +35,7 @@ constexpr int TNP = 256;                 // columns of the pair's tile: each CTA
 constexpr int TK = 32;
 constexpr int T_H = TM * TK * 2;         // one fp16 tile: 128 rows x 64 bytes (SWIZZLE_64B)
 constexpr int OPB = 4 * T_H;             // ring slot: A_hi | A_lo | W_hi | W_lo
-constexpr int EPI_WARPS = 8, EPI_WARP0 = 2, THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int EPI_WARP0 = 2;              // w0 TMA producer, w1 MMA issuer, then the epilogue warps
 constexpr int EP = 34;                   // floats per transpose-buffer row
 constexpr int BAR_BYTES = 256;
 constexpr uint32_t ACC_COLS = TNP, TMEM_COLS = 2 * ACC_COLS;
@@ -44,9 +44,15 @@ constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(TNP >> 3) << 17) | ((uint32_
 
 template <int MODE>
 struct ECfg {
+    // Epilogue warps.  Block 1's epilogue is latency-bound per warp (TMEM read -> gathers -> SiLU -> split -> staging ->
+    // TMA store); with the MMAs pacing the steady state what it costs is the exposed tail after each CTA's last tile
+    // (18k of 98k cycles with 8 warps): it works in 16-column groups (112 registers) so that 16 warps fit.  Block 2
+    // (transposes + segment sums, 32-column chunks) keeps 8: with 16 its ring would shrink to 4 slots (measured slower).
+    static constexpr int EPI_WARPS = MODE == 0 ? 16 : 8;
+    static constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
     static constexpr int S = MODE == 0 ? 6 : 5;                                   // ring depth
-    // block 2: per-warp transpose buffers; block 1: per-warp staging of a 32 x 32 (hi, lo) fp16 output chunk for TMA stores
-    static constexpr int EBUF_BYTES = MODE == 0 ? EPI_WARPS * 4096 : EPI_WARPS * 32 * EP * 4;
+    // block 2: per-warp transpose buffers; block 1: per-warp staging of a 32 x 16 (hi, lo) fp16 output group for TMA stores
+    static constexpr int EBUF_BYTES = MODE == 0 ? EPI_WARPS * 2048 : EPI_WARPS * 32 * EP * 4;
     static constexpr int RING_BYTES = S * OPB;
     static constexpr int SMEM_BYTES = RING_BYTES + EBUF_BYTES + BAR_BYTES;
     static_assert(SMEM_BYTES <= 232448, "does not fit the SM");
@@ -108,7 +114,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-// TMA store of a [32 rows x 32 columns] fp16 tile (SWIZZLE_64B in shared memory); rows / columns past the tensor are clipped
+// TMA store of a [32 rows x 16 columns] fp16 tile (SWIZZLE_32B in shared memory); rows / columns past the tensor are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -152,12 +158,12 @@ __device__ __forceinline__ void scatter_chunk(const float* ebuf, uint32_t starts
 
 // MODE 0: block 1 (gathers + SiLU, pre-split output).  MODE 1: block 2 (bias + SiLU + scatter-mean).
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((ECfg<MODE>::THREADS), 1)
 edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                  const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                  const __grid_constant__ CUtensorMap mapOh, const __grid_constant__ CUtensorMap mapOl, const EdgeParams p) {
     using C = ECfg<MODE>;
-    constexpr int S = C::S;
+    constexpr int S = C::S, EPI_WARPS = C::EPI_WARPS;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* ring = smem;
     float* ebuf_all = reinterpret_cast<float*>(smem + C::RING_BYTES);
@@ -273,7 +279,7 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
     } else {
         // ===================== epilogue warps (w2..9), overlapped with the next tile's main loop =====================
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int cg = (warp - EPI_WARP0) >> 2;                   // column half of the tile: four 32-column chunks
+        const int cg = (warp - EPI_WARP0) >> 2;                   // column group of the tile: 256 / (EPI_WARPS / 4) columns
         float* ebuf = ebuf_all + (warp - EPI_WARP0) * (32 * EP);
         (void)ebuf;
         for (int tl = 0; tl < my_tiles; ++tl) {
@@ -282,9 +288,11 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
             const uint32_t ab = (uint32_t)tl & 1;
             const int mrow = m0 + (int)rank * TM + q * 32 + lane;       // the row this lane owns in TMEM
             const bool ok = mrow < p.M;
-            const uint32_t tbase = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 128);
+            constexpr int WCOLS = TNP / (EPI_WARPS / 4);          // columns per warp: 64 (block 1), 128 (block 2)
+            const uint32_t tbase = tmem_base + ab * ACC_COLS + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * WCOLS);
             const uint32_t ae = mapa_rank(smem_u32(&acc_empty[ab]), 0);
             uint32_t v[32];
+            (void)v;
             if (MODE == 0) {
                 // bound of the row maximum -> power-of-two scale of the fp16 pair; consumers derive the same exponent
                 int i1 = 0, i2 = 0;
@@ -302,51 +310,51 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                 if (threadIdx.x == 64) ETRACE(tl, 6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int n = n0 + cg * 128 + cc * 32;
-                    tmem_ld32(tbase + (uint32_t)(cc * 32), v);
-                    float gp[32], gq[32];                // the two gathered rows: in flight behind the TMEM read
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        ldnc8(prow + n + j, gp + j);
-                        ldnc8(qrow + n + j, gq + j);
-                    }
+                for (int gi = 0; gi < WCOLS / 16; ++gi) {
+                    const int n = n0 + cg * WCOLS + gi * 16;
+                    uint32_t v16[16];
+                    tmem_ld16(tbase + (uint32_t)(gi * 16), v16);
+                    float gp[16], gq[16];                // the two gathered rows: in flight behind the TMEM read
+                    ldnc8(prow + n, gp);
+                    ldnc8(prow + n + 8, gp + 8);
+                    ldnc8(qrow + n, gq);
+                    ldnc8(qrow + n + 8, gq + 8);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cc == 3) {                      // all of this warp's TMEM reads are done: release the accumulators
+                    if (gi == WCOLS / 16 - 1) {         // all of this warp's TMEM reads are done: release the accumulators
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(ae);
                     }
-                    uint32_t hi[16], lo[16];
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 16; j += 4) {
                         const float4 cs = __ldg(reinterpret_cast<const float4*>(p.col_scale + n + j));
                         const float c4[4] = {cs.x, cs.y, cs.z, cs.w};
                         float a[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            a[u] = silu_fast(fmaf(p.alpha * __uint_as_float(v[j + u]), c4[u], gp[j + u] + gq[j + u])) * osc;
+                            a[u] = silu_fast(fmaf(p.alpha * __uint_as_float(v16[j + u]), c4[u], gp[j + u] + gq[j + u])) * osc;
                         split2<1>(a[0], a[1], hi[j / 2], lo[j / 2]);
                         split2<1>(a[2], a[3], hi[j / 2 + 1], lo[j / 2 + 1]);
                     }
-                    // The chunk leaves through TMA: a row-per-lane global store costs one L1 wavefront per lane and instruction
-                    // (128 per chunk, a third of this epilogue's L1 time, and the epilogue paces this kernel:
-                    // scripts/trace_edge.py); 16-byte swizzled shared-memory stores cost 4.
-                    uint8_t* sh = reinterpret_cast<uint8_t*>(ebuf_all) + (warp - EPI_WARP0) * 4096;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous chunk has left the buffer
+                    // The group leaves through TMA: a row-per-lane global store costs one L1 wavefront per lane and instruction
+                    // (a third of this epilogue's L1 time when it paced the kernel: scripts/trace_edge.py); 16-byte swizzled
+                    // shared-memory stores cost 4.
+                    uint8_t* sh = reinterpret_cast<uint8_t*>(ebuf_all) + (warp - EPI_WARP0) * 2048;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous group has left the buffer
                     __syncwarp();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int off = lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);      // SWIZZLE_64B: 16-byte chunk ^ (row / 2) % 4
+                    for (int c = 0; c < 2; ++c) {
+                        const int off = lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4);      // SWIZZLE_32B: 16-byte chunk ^ (row / 4) % 2
                         *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(sh + 2048 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(sh + 1024 + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         const int r0_ = m0 + (int)rank * TM + q * 32;
                         tma_store_2d(&mapOh, sh, n, r0_);
-                        tma_store_2d(&mapOl, sh + 2048, n, r0_);
+                        tma_store_2d(&mapOl, sh + 1024, n, r0_);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -418,8 +426,8 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
     if ((rc = mi_tc_make_map(&mWl, W_lo, p.N, p.K, ldw, TNP / 2, true)) != MI_OK) return rc;
     CUtensorMap mOh = mAh, mOl = mAl;                             // block 2 has no tensor output
     if (MODE == 0) {
-        if ((rc = mi_tc_make_map(&mOh, p.out_hi, p.M, p.N, p.ld_out, 32, true)) != MI_OK) return rc;
-        if ((rc = mi_tc_make_map(&mOl, p.out_lo, p.M, p.N, p.ld_out, 32, true)) != MI_OK) return rc;
+        if ((rc = mi_tc_make_map_h16(&mOh, p.out_hi, p.M, p.N, p.ld_out, 32)) != MI_OK) return rc;
+        if ((rc = mi_tc_make_map_h16(&mOl, p.out_lo, p.M, p.N, p.ld_out, 32)) != MI_OK) return rc;
     }
     static bool attr = false;
     if (!attr) {
@@ -437,7 +445,7 @@ int launch_pair(const void* A_hi, const void* A_lo, int lda, const void* W_hi, c
     if (tiles < pairs) pairs = tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = s;
     cudaLaunchAttribute at[1];

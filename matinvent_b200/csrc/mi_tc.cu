@@ -793,6 +793,21 @@ int make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long ro
 }  // namespace
 
 int mi_tc_get_encode() { return get_encode(); }
+// 2-D fp16 map with a [box_rows, 16 columns] box (32-byte rows, SWIZZLE_32B): the store tiles of 16-column epilogue groups
+int mi_tc_make_map_h16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mi_set_error_("cuTensorMapEncodeTiled failed (%d) for the fp16 store map [%lld,%lld] ld %lld", (int)r, rows, cols, ld);
+        return MI_ERR_CUDA;
+    }
+    return MI_OK;
+}
 int mi_tc_make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld, int box_rows) {
     return make_map_pair(map, hi, lo, rows, cols, ld, box_rows);
 }

@@ -155,5 +155,6 @@ inline bool mi_pdl_enabled() {
     return on != 0;
 }
 int mi_tc_make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, bool half);
+int mi_tc_make_map_h16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
 // one 3-D map over an fp16 (hi, lo) operand pair (lo follows hi by a multiple of 16 bytes): box = [2, box_rows, 32 columns]
 int mi_tc_make_map_pair(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld, int box_rows);
