@@ -123,6 +123,25 @@ def postprocess(outputs):
     return data
 
 
+def pack_crystals(data_list):
+    """a list of CrystalData as five concatenated CPU tensors (one pickle of five tensors instead of five per crystal when
+    sampled crystals travel between ranks)"""
+    if not data_list:
+        return None
+    return (torch.cat([d.frac_coords for d in data_list]), torch.cat([d.atom_types for d in data_list]),
+            torch.cat([d.lengths for d in data_list]), torch.cat([d.angles for d in data_list]),
+            torch.tensor([int(d.num_atoms) for d in data_list], dtype=torch.int64))
+
+
+def unpack_crystals(pack):
+    if pack is None:
+        return []
+    x, z, lengths, angles, na = pack
+    off = [0] + torch.cumsum(na, 0).tolist()
+    return [CrystalData(x[off[i]:off[i + 1]], z[off[i]:off[i + 1]], lengths[i].view(1, -1), angles[i].view(1, -1), na[i])
+            for i in range(len(na))]
+
+
 @dataclass
 class DiffCSPSampler:
     batch_size: int | None = None

@@ -70,7 +70,7 @@ class MatInvent(ReinL):
         if world > 1:
             from ..models.diffcsp.diffusion import PhiloxNoise
             from ..models.diffcsp.finetune import partition_crystals
-            from ..models.diffcsp.sample import SampleDataset
+            from ..models.diffcsp.sample import SampleDataset, pack_crystals, to_structure, unpack_crystals
             import torch
             counts = SampleDataset(bs * nb, self.sampler.num_atoms_distribution).num_atoms.tolist()
             data, strucs = [], []
@@ -81,14 +81,16 @@ class MatInvent(ReinL):
                 chunk = [max(int(n), 1) for n in counts[b * bs:(b + 1) * bs]]
                 lo, hi = partition_crystals(chunk, world)[rank]
                 if hi > lo:
-                    d, s_ = self.sampler.generate(self.agent, batch_size=hi - lo, num_batches=1, noise=noise,
-                                                  num_atoms=chunk[lo:hi], **cfg)
+                    d, _ = self.sampler.generate(self.agent, batch_size=hi - lo, num_batches=1, noise=noise,
+                                                 num_atoms=chunk[lo:hi], **cfg)
                 else:
-                    d, s_ = [], []
+                    d = []
+                # the shard travels as five concatenated tensors (one small pickle per rank, not five tensors per crystal)
                 gathered = [None] * world
-                dist.all_gather_object(gathered, (d, s_))
-                data += [x for part in gathered for x in part[0]]
-                strucs += [x for part in gathered for x in part[1]]
+                dist.all_gather_object(gathered, pack_crystals(d))
+                part = [x for g_ in gathered for x in unpack_crystals(g_)]
+                data += part
+                strucs += [to_structure(x) for x in part]
         else:
             data, strucs = self.sampler.generate(self.agent, batch_size=bs, num_batches=nb, noise=self.noise, **cfg)
         self.timing["sample_s"] = time.time() - t0

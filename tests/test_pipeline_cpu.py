@@ -59,3 +59,18 @@ def test_pipeline_oracle_known_answers():
     v = P.composition_property([14, 8, 8], tab, mass, "mass")
     assert abs(v - (28.085 * 1000 + 31.998 * 500) / 60.083) < 1e-9
     assert abs(P.composition_property([14, 8, 8], tab, mass, "atom") - (1000 + 2 * 500) / 3) < 1e-9
+
+
+def test_pack_unpack_crystals_roundtrip():
+    """the inter-rank transport of sampled crystals (MatInvent.sample_step): five concatenated tensors per shard"""
+    import torch
+    from matinvent_b200.models.diffcsp.sample import CrystalData, pack_crystals, unpack_crystals
+    g = torch.Generator().manual_seed(0)
+    data = [CrystalData(torch.rand(n, 3, generator=g), torch.randint(1, 101, (n,), generator=g), torch.rand(1, 3, generator=g),
+                        torch.rand(1, 3, generator=g), torch.tensor(n)) for n in (3, 1, 20, 7)]
+    back = unpack_crystals(pack_crystals(data))
+    assert len(back) == len(data)
+    for a, b in zip(data, back):
+        assert torch.equal(a.frac_coords, b.frac_coords) and torch.equal(a.atom_types, b.atom_types)
+        assert torch.equal(a.lengths, b.lengths) and torch.equal(a.angles, b.angles) and int(a.num_atoms) == int(b.num_atoms)
+    assert unpack_crystals(pack_crystals([])) == []
