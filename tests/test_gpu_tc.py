@@ -366,6 +366,48 @@ def test_node_chain_matches_separate_kernels(gold_full, num_atoms):
 
 
 # ---------------------------------------------------------------- CTA-pair per-edge blocks (csrc/mi_edge.cu)
+def test_edge_pair_blocks_tile_boundaries():
+    """edge counts at and around the 256-row pair tile and the 128-row CTA half (1, 127, 128, 129, 255, 256, 257, 512 rows):
+    rows past the last tile are clipped by the TMA stores and skipped by the scatter, nothing outside the outputs is touched"""
+    import math
+    from matinvent_b200 import ops
+    H, K1, nn = 512, 768, 40
+    g = torch.Generator().manual_seed(9)
+    WF, W2 = _rand(H, K1, seed=6) / K1 ** 0.5, _rand(H, H, seed=7) / H ** 0.5
+    fh, fl = torch.empty_like(WF, dtype=torch.float16), torch.empty_like(WF, dtype=torch.float16)
+    wh, wl = torch.empty_like(W2, dtype=torch.float16), torch.empty_like(W2, dtype=torch.float16)
+    finv, winv = torch.empty(H, device="cuda"), torch.empty(H, device="cuda")
+    ops.f16_split_rows(WF, fh, fl, finv)
+    ops.f16_split_rows(W2, wh, wl, winv)
+    wfb = (math.sqrt(K1 / 2) * WF.norm(dim=1).max() * 1.001).reshape(1).contiguous()
+    pqr = _rand(nn, 3 * H, seed=9).contiguous()
+    amax_pq = pqr.abs().amax(1).contiguous()
+    for E in (1, 127, 128, 129, 255, 256, 257, 512):
+        src = torch.sort(torch.randint(0, nn, (E,), generator=g)).values
+        dst = torch.randint(0, nn, (E,), generator=g)
+        ang = (torch.rand(E, K1 // 2, generator=g) * 2 * math.pi).cuda()
+        phi = torch.cat([ang.sin(), ang.cos()], dim=1).contiguous()
+        ph = (phi * 2.0 ** 14).half()
+        pl = (phi * 2.0 ** 14 - ph.float()).half()
+        a1 = torch.full((2, E + 3, H), 7.0, device="cuda", dtype=torch.float16)          # three guard rows behind the tensor
+        bound = torch.full((E + 3,), 7.0, device="cuda")
+        ops.edge_block1(E, ph, pl, fh, fl, finv, 2.0 ** -14, pqr[:, :H], pqr[:, H:2 * H], src.int().cuda(), dst.int().cuda(), amax_pq,
+                        wfb, a1[0][:E], a1[1][:E], bound[:E])
+        assert float((a1[:, E:].float() - 7.0).abs().max()) == 0.0 and float((bound[E:] - 7.0).abs().max()) == 0.0
+        z1 = phi.double() @ WF.double().t() + pqr[:, :H].double()[src.cuda()] + pqr[:, H:2 * H].double()[dst.cuda()]
+        e8 = torch.floor(torch.log2(bound[:E])) - 14
+        got1 = (a1[0][:E].double() + a1[1][:E].double()) * torch.exp2(e8.double())[:, None]
+        err1 = float(((got1 - torch.nn.functional.silu(z1)).abs().amax(1) / z1.abs().amax(1)).max())
+        cnt = torch.bincount(src, minlength=nn).clamp_min(1)
+        w = (1.0 / cnt.float())[src].cuda()
+        out = torch.zeros(nn + 2, H, device="cuda")
+        ops.edge_block2(E, a1[0][:E], a1[1][:E], bound[:E], wh, wl, winv, None, out[:nn], src.int().cuda(), w, None)
+        y = torch.nn.functional.silu(got1 @ W2.double().t())
+        ref = torch.zeros(nn, H, dtype=torch.float64, device="cuda").index_add_(0, src.cuda(), y) / cnt.double().cuda()[:, None]
+        err2 = float((out[:nn].double() - ref).abs().max() / ref.abs().max())
+        assert err1 < 6e-6 and err2 < 8e-6 and float(out[nn:].abs().max()) == 0.0, (E, err1, err2)
+
+
 @pytest.mark.parametrize("crystals,spread", [(3, 0.0), (40, 0.0), (230, 3.0), (900, 0.0)])
 def test_edge_pair_blocks_vs_float64(crystals, spread):
     """mi_edge_block1 -> mi_edge_block2 (tcgen05.mma.cta_group::2, both operands staged by TMA, a1 handed over as an fp16
