@@ -58,11 +58,15 @@ class _Workspace:
         # inference: the embedding output keeps its own buffer (the predictor forward of a reverse step reuses the
         # corrector's: same atom-type state, time and lattice), the layers update one shared buffer in place
         self.h = [buf(N, H) for _ in range(L + 1)] if train else [buf(N, H)] + [buf(N, H)] * L
-        self.cat = [buf(N, 2 * H) for _ in range(nl)]
+        self.cat = [torch.zeros(N, 2 * H, device=dev, dtype=f32) for _ in range(nl)]
         # [P' | Q | R]: the per-node parts of the first edge linear and, third block, the LN(h) half of node_mlp.0
         # (forward_graph, "node path"); the FP32 / unfused path uses the first two blocks only
         self.pqr = buf(N, 3 * H)
         self.pq = self.pqr[:, :2 * H]
+        # layer 0's [P'|Q|R] and its row maxima keep their own buffers: they depend on (atom types, time, lattice) only, so
+        # the predictor evaluation of a reverse step reuses the corrector's (forward_graph(reuse_embedding=True))
+        self.pqr0 = buf(N, 3 * H)
+        self.amax_pqr0 = torch.zeros(N, device=dev, dtype=f32)
         self.hn_hi = torch.empty(N, H, device=dev, dtype=torch.float16)      # LN(h) as a pre-split tensor-core operand
         self.hn_lo = torch.empty(N, H, device=dev, dtype=torch.float16)
         # operand pairs written by the node chain's epilogues (mi_node_chain): xs = split(agg) / split(LN(h)), ys = split(an1)
@@ -505,16 +509,17 @@ class CSPNet(nn.Module):
         [P'|Q|R] the LayerNorm'd node path reports (ws.amax_pqr)"""
         return merged and not train and self.use_pair and self.use_tc and self.ln and self.hidden_dim % 256 == 0
 
-    def edge_gemm1(self, i, ws, g, E, a1, train, presplit, merged):
+    def edge_gemm1(self, i, ws, g, E, a1, train, presplit, merged, pqr=None, amax_pqr=None):
         """a1 = silu(Phi W_F^T + P'[src] + Q[dst])   (first edge linear, cspnet.py:59-72, per-edge part)"""
         H, q = self.hidden_dim, "l%d." % i
+        pqr = ws.pqr if pqr is None else pqr
         if self.pair_mode(train, merged):
             a1h, a1l = a1.view(torch.float16).view(2, -1, H)[:, :a1.shape[0]]
             ops.edge_block1(E, ws.phi_hi, ws.phi_lo, self._mhi[q + "w_f"], self._mlo[q + "w_f"], self._minv[q + "w_f"], 2.0 ** -14,
-                            ws.pq[:, :H], ws.pq[:, H:], g.edge_src, g.edge_dst, ws.amax_pqr[i], self._bounds[i, 3:4], a1h, a1l,
-                            ws.amax_a1[i])
+                            pqr[:, :H], pqr[:, H:2 * H], g.edge_src, g.edge_dst, ws.amax_pqr[i] if amax_pqr is None else amax_pqr,
+                            self._bounds[i, 3:4], a1h, a1l, ws.amax_a1[i])
             return
-        epi1 = dict(gathers=[(ws.pq[:, :H], g.edge_src), (ws.pq[:, H:], g.edge_dst)],
+        epi1 = dict(gathers=[(pqr[:, :H], g.edge_src), (pqr[:, H:2 * H], g.edge_dst)],
                     z_out=ws.z1[i] if train else None, act=ACT_SILU, amax_out=ws.amax_a1[i])
         if merged:
             ops.tc_gemm_presplit(ws.phi_hi, ws.phi_lo, self._mhi[q + "w_f"], self._mlo[q + "w_f"], a1, M=E,
@@ -601,20 +606,26 @@ class CSPNet(nn.Module):
             h_in, h_out = ws.h[i], ws.h[i + 1]
             hn, agg = cat[:, :H], cat[:, H:]
             if chain:
-                if i == 0:
+                pqr_i, amax_i = (ws.pqr0, ws.amax_pqr0) if i == 0 else (ws.pqr, ws.amax_pqr[i])
+                if i == 0 and not reuse:
+                    # layer 0's LayerNorm and [P'|Q|R] see the embedding output only (atom types, time, lattice): the
+                    # predictor evaluation of a reverse step reuses the corrector's
+                    ws.amax_pqr0.zero_()
                     ops.layernorm_fwd_split(h_in, W[q + "ln_g"], W[q + "ln_b"], None, ws.hn_hi, ws.hn_lo, ws.amax_hn[i], N, H,
                                             zero_out=agg if merged else None, zero_cols=H)
-                    ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr, M=N,
-                                         gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i], amax_out=ws.amax_pqr[i])
-                self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged)
+                    ops.tc_gemm_presplit(ws.hn_hi, ws.hn_lo, self._pqr_hi[i], self._pqr_lo[i], ws.pqr0, M=N,
+                                         gathers=[(ws.cb[i], g.node_graph)], a_amax=ws.amax_hn[i], amax_out=ws.amax_pqr0)
+                self.edge_gemm1(i, ws, g, E, a1, train, presplit, merged, pqr=pqr_i, amax_pqr=amax_i)
                 self.edge_gemm2(i, ws, g, E, a1, agg, train, merged)
                 nxt = None
                 if i + 1 < L:
                     qn = "l%d." % (i + 1)
                     nxt = (W[qn + "ln_g"], W[qn + "ln_b"], 1e-5, self._pqr_hi[i + 1], self._pqr_lo[i + 1], ws.cb[i + 1],
                            g.node_graph, ws.pqr, ws.amax_pqr[i + 1])
-                ops.node_chain(N, H, agg, ws.amax_agg[i], merged and i + 1 < L, ws.xs, ws.ys, self._hi[q + "wn1"][:, H:],
-                               self._lo[q + "wn1"][:, H:], W[q + "bn1"], ws.pqr[:, 2 * H:], ws.amax_pqr[i], self._bounds[i],
+                # (agg is zeroed after every layer, the last one included: it is the zeroed destination of the next
+                # evaluation's first fused scatter-mean, whose LayerNorm launch is skipped when the embedding is reused)
+                ops.node_chain(N, H, agg, ws.amax_agg[i], merged, ws.xs, ws.ys, self._hi[q + "wn1"][:, H:],
+                               self._lo[q + "wn1"][:, H:], W[q + "bn1"], pqr_i[:, 2 * H:], amax_i, self._bounds[i],
                                self._hi[q + "wn2"], self._lo[q + "wn2"], W[q + "bn2"], h_in, h_out, ln=nxt)
                 continue
             # edge model (cspnet.py:59-75) with the first linear split into per-node / per-crystal / per-edge parts; the
