@@ -349,41 +349,56 @@ __global__ void __launch_bounds__(256, 2) output_heads_kernel(const float* __res
                 for (int r = 0; r < nrow; ++r) a += hs[r * H + c];
                 colsum[c] = a;
             }
+        auto wrow = [&](int o) {                       // weight row of output column o (coordinate head first); past the end: row 0
+            const bool is_x_ = pred_x && o < 3;
+            const int oc_ = is_x_ ? o : o - (pred_x ? 3 : 0);
+            if (o >= n_out) return pred_x ? coord_w : type_w;
+            return is_x_ ? coord_w + (long long)oc_ * H : type_w + (long long)oc_ * H;
+        };
         const int nrow4 = (nrow + 3) & ~3;
-        for (int o = warp; o < n_out; o += nw) {      // one output column per warp: weight row in registers
-            const bool is_x = pred_x && o < 3;
-            const int oc = is_x ? o : o - (pred_x ? 3 : 0);
-            const float* wr = is_x ? coord_w + (long long)oc * H : type_w + (long long)oc * H;
-            float wv[NV];
+        // register tile: 4 output columns x 4 rows per warp step — every row is read from shared memory once per FOUR
+        // output columns (one column at a time made this kernel shared-memory bound: 64 loads per 64 FMAs)
+        for (int ob = warp * 4; ob < n_out; ob += nw * 4) {
+            float wv[4][NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) wv[i] = __ldg(wr + lane + 32 * i);
-            const float bias = (!is_x && type_b) ? __ldg(type_b + oc) : 0.f;
-            for (int r = 0; r < nrow4; r += 4) {      // four rows at a time: independent FMA chains, one shared reduction
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                const float* wr = wrow(ob + c);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) wv[c][i] = __ldg(wr + lane + 32 * i);
+            }
+            for (int r = 0; r < nrow4; r += 4) {
+                float d[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) d[k] = 0.f;
                 const float* hr = hs + r * H + lane;
 #pragma unroll
                 for (int i = 0; i < NV; ++i) {
-                    d0 = fmaf(hr[32 * i], wv[i], d0);
-                    d1 = fmaf(hr[H + 32 * i], wv[i], d1);
-                    d2 = fmaf(hr[2 * H + 32 * i], wv[i], d2);
-                    d3 = fmaf(hr[3 * H + 32 * i], wv[i], d3);
+                    const float x0 = hr[32 * i], x1 = hr[H + 32 * i], x2 = hr[2 * H + 32 * i], x3 = hr[3 * H + 32 * i];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        d[c] = fmaf(x0, wv[c][i], d[c]);
+                        d[4 + c] = fmaf(x1, wv[c][i], d[4 + c]);
+                        d[8 + c] = fmaf(x2, wv[c][i], d[8 + c]);
+                        d[12 + c] = fmaf(x3, wv[c][i], d[12 + c]);
+                    }
                 }
-                // reduce-scatter over the lanes: after two exchange steps every lane holds one of the four sums' halves
-                const bool up16 = lane & 16, up8 = lane & 8;
-                float s0 = up16 ? d2 : d0, s1 = up16 ? d3 : d1;               // keep rows {0,1} in the lower half, {2,3} in the upper
-                float t0 = up16 ? d0 : d2, t1 = up16 ? d1 : d3;
-                s0 += __shfl_xor_sync(0xffffffffu, t0, 16);
-                s1 += __shfl_xor_sync(0xffffffffu, t1, 16);
-                float u = up8 ? s1 : s0, w_ = up8 ? s0 : s1;
-                u += __shfl_xor_sync(0xffffffffu, w_, 8);
-                u += __shfl_xor_sync(0xffffffffu, u, 4);
-                u += __shfl_xor_sync(0xffffffffu, u, 2);
+                // reduce-scatter of the 16 sums over the lanes: lane l ends with sum number (l >> 1) & 15 = row * 4 + column
+                float e8[8], e4[4], e2[2];
+                const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e8[k] = (b4 ? d[8 + k] : d[k]) + __shfl_xor_sync(0xffffffffu, b4 ? d[k] : d[8 + k], 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) e4[k] = (b3 ? e8[4 + k] : e8[k]) + __shfl_xor_sync(0xffffffffu, b3 ? e8[k] : e8[4 + k], 8);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) e2[k] = (b2 ? e4[2 + k] : e4[k]) + __shfl_xor_sync(0xffffffffu, b2 ? e4[k] : e4[2 + k], 4);
+                float u = (b1 ? e2[1] : e2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? e2[0] : e2[1], 2);
                 u += __shfl_xor_sync(0xffffffffu, u, 1);
-                // lanes 0 / 8 / 16 / 24 hold rows r + 0 / 1 / 2 / 3
-                const int rr = r + ((lane >> 4) << 1) + ((lane >> 3) & 1);
-                if ((lane & 7) == 0 && rr < nrow) {
+                const int idx = (lane >> 1) & 15, rr = r + (idx >> 2), o = ob + (idx & 3);
+                if ((lane & 1) == 0 && rr < nrow && o < n_out) {
+                    const bool is_x = pred_x && o < 3;
+                    const int oc = is_x ? o : o - (pred_x ? 3 : 0);
                     if (is_x) pred_x[(long long)(c0 + rr) * 3 + oc] = u;
-                    else pred_a[(long long)(c0 + rr) * A + oc] = u + bias;
+                    else pred_a[(long long)(c0 + rr) * A + oc] = u + (type_b ? __ldg(type_b + oc) : 0.f);
                 }
             }
         }
