@@ -225,55 +225,63 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
-            for (uint32_t it = 0; it < total; ++it) {
-                const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
-                int m0, n0;
-                tile_origin(tl, m0, n0);
-                const int s = (int)(it % (uint32_t)S);
-                mbar_wait(&empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+        // All lanes run the loop, one elected lane issues (mi_tc_common.cuh, elect_one(): inside an `if (lane == 0)` region
+        // every TMA / MMA instruction is wrapped in a R2UR.BROADCAST loop, ~170 cycles per TMA operation, ~90 per MMA)
+        for (uint32_t it = 0; it < total; ++it) {
+            const int tl = (int)(it / (uint32_t)nkb), kb = (int)(it % (uint32_t)nkb);
+            int m0, n0;
+            tile_origin(tl, m0, n0);
+            const int s = (int)(it % (uint32_t)S);
+            mbar_wait(&empty[s], ((it / (uint32_t)S) & 1) ^ 1);
+            if (lane == 0) {
                 if (kb == 0) ETRACE(tl, 0);
                 if (kb == nkb - 1) ETRACE(tl, 1);
-                uint8_t* st = ring + s * OPB;
-                const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
+            }
+            uint8_t* st = ring + s * OPB;
+            const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
+            const int kc = kb * TK, ma = m0 + (int)rank * TM, nw = n0 + (int)rank * (TNP / 2);
+            if (elect_one()) {
                 mbar_expect_tx_cluster(fb, OPB);
-                const int kc = kb * TK, ma = m0 + (int)rank * TM, nw = n0 + (int)rank * (TNP / 2);
                 tma_load_2d_pair(st, &mapAh, fb, kc, ma);
                 tma_load_2d_pair(st + T_H, &mapAl, fb, kc, ma);
                 tma_load_2d_pair(st + 2 * T_H, &mapWh, fb, kc, nw);
                 tma_load_2d_pair(st + 3 * T_H, &mapWl, fb, kc, nw);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {                                          // all lanes run the loop, one elected lane issues
             uint32_t it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const uint32_t ab = (uint32_t)tl & 1;
                 const uint32_t acc = tmem_base + ab * ACC_COLS;
-                ETRACE(tl, 2);
+                if (lane == 0) ETRACE(tl, 2);
                 mbar_wait(&acc_empty[ab], (((uint32_t)tl >> 1) & 1) ^ 1);
-                ETRACE(tl, 3);
+                if (lane == 0) ETRACE(tl, 3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = (int)(it % (uint32_t)S);
                     mbar_wait(&full[s], (it / (uint32_t)S) & 1);
-                    if (kb == 0) ETRACE(tl, 4);
+                    if (kb == 0 && lane == 0) ETRACE(tl, 4);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(ring + s * OPB);
                     const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + T_H);
                     const uint64_t d_whi = umma_desc(st + 2 * T_H), d_wlo = umma_desc(st + 3 * T_H);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                        umma_f16_pair(acc, d_ahi + adv, d_whi + adv, IDESC2, (kb | k) != 0);
-                        umma_f16_pair(acc, d_alo + adv, d_whi + adv, IDESC2, 1u);
-                        umma_f16_pair(acc, d_ahi + adv, d_wlo + adv, IDESC2, 1u);
+                        for (int k = 0; k < TK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_f16_pair(acc, d_ahi + adv, d_whi + adv, IDESC2, (kb | k) != 0);
+                            umma_f16_pair(acc, d_alo + adv, d_whi + adv, IDESC2, 1u);
+                            umma_f16_pair(acc, d_ahi + adv, d_wlo + adv, IDESC2, 1u);
+                        }
+                        umma_commit_pair(&empty[s]);
+                        if (kb == nkb - 1) umma_commit_pair(&acc_full[ab]);
                     }
-                    umma_commit_pair(&empty[s]);
+                    __syncwarp();
                 }
-                umma_commit_pair(&acc_full[ab]);
-                ETRACE(tl, 5);
+                if (lane == 0) ETRACE(tl, 5);
             }
         }
     } else {

@@ -224,16 +224,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // One thread feeds both rings: W (and pre-split A) for k-block i as soon as its op slot is free, raw A for
         // k-block i + R - 1 as soon as the split warps have released that raw slot — raw tiles run ahead of the
         // op ring, which is what hides the HBM latency of A.
-        if (lane == 0) {
-            TRACE(0, 14);
+        // (All lanes run the loops, one elected lane issues: inside an `if (lane == 0)` region the compiler wraps every TMA /
+        // MMA instruction in a R2UR.BROADCAST loop — see elect_one() in mi_tc_common.cuh.)
+        {
+            if (lane == 0) TRACE(0, 14);
             auto issue_raw = [&](uint32_t idx) {
                 const int tl = (int)(idx / (uint32_t)nkb), kb = (int)(idx % (uint32_t)nkb);
                 int m0, n0, kb0;
                 tile_origin4(tl, m0, n0, kb0);
                 const int r = (int)(idx % (uint32_t)RR);
                 mbar_wait(&raw_empty[r], ((idx / (uint32_t)RR) & 1) ^ 1);
-                mbar_expect_tx(&raw_full[r], A_RAW);
-                tma_load_2d(raw_ring + r * A_RAW, &mapA, &raw_full[r], (kb0 + kb) * TK, m0);
+                if (elect_one()) {
+                    mbar_expect_tx(&raw_full[r], A_RAW);
+                    tma_load_2d(raw_ring + r * A_RAW, &mapA, &raw_full[r], (kb0 + kb) * TK, m0);
+                }
+                __syncwarp();
             };
             uint32_t a_it = 0;
             if (!PRESPLIT)
@@ -245,49 +250,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int kc = (kb0 + kb) * TK;
                 const int s = (int)(it % (uint32_t)S);
                 mbar_wait(&op_empty[s], ((it / (uint32_t)S) & 1) ^ 1);
-                if (kb == 0) TRACE(tl, 0);
+                if (kb == 0 && lane == 0) TRACE(tl, 0);
                 uint8_t* st = op_ring + s * OPB;
-                mbar_expect_tx(&w_full[s], (PRESPLIT ? 2 * A_H : 0) + 2 * W_H);
-                if (PRESPLIT) {
-                    tma_load_2d(st, &mapA, &w_full[s], kc, m0);
-                    tma_load_2d(st + A_H, &mapAlo, &w_full[s], kc, m0);
+                if (elect_one()) {
+                    mbar_expect_tx(&w_full[s], (PRESPLIT ? 2 * A_H : 0) + 2 * W_H);
+                    if (PRESPLIT) {
+                        tma_load_2d(st, &mapA, &w_full[s], kc, m0);
+                        tma_load_2d(st + A_H, &mapAlo, &w_full[s], kc, m0);
+                    }
+                    tma_load_2d(st + 2 * A_H, &mapWhi, &w_full[s], kc, n0);
+                    tma_load_2d(st + 2 * A_H + W_H, &mapWlo, &w_full[s], kc, n0);
                 }
-                tma_load_2d(st + 2 * A_H, &mapWhi, &w_full[s], kc, n0);
-                tma_load_2d(st + 2 * A_H + W_H, &mapWlo, &w_full[s], kc, n0);
+                __syncwarp();
                 if (!PRESPLIT && a_it < total) issue_raw(a_it++);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             uint32_t it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const uint32_t ab = (uint32_t)tl & 1;            // accumulator buffer of this tile
                 const uint32_t acc = tmem_base + ab * C::ACC_COLS;
                 mbar_wait(&acc_empty[ab], (((uint32_t)tl >> 1) & 1) ^ 1);   // the tile two back has been read out of this buffer
-                TRACE(tl, 1);
+                if (lane == 0) TRACE(tl, 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = (int)(it % (uint32_t)S);
                     const uint32_t ph = (it / (uint32_t)S) & 1;
                     mbar_wait(&w_full[s], ph);
                     if (!PRESPLIT) mbar_wait(&a_ready[s], ph);
-                    if (kb == 0) TRACE(tl, 2);
+                    if (kb == 0 && lane == 0) TRACE(tl, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t st = smem_u32(op_ring + s * OPB);
                     const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + A_H);
                     const uint64_t d_whi = umma_desc(st + 2 * A_H), d_wlo = umma_desc(st + 2 * A_H + W_H);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < TK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
-                        umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
-                        umma_f16(acc + CORR, d_alo + adv, d_whi + adv, IDESC, MERGED ? 1u : (uint32_t)((kb | k) != 0));
-                        umma_f16(acc + CORR, d_ahi + adv, d_wlo + adv, IDESC, 1u);
+                        for (int k = 0; k < TK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);      // 16 fp16 = 32 bytes along the swizzled row
+                            umma_f16(acc, d_ahi + adv, d_whi + adv, IDESC, (kb | k) != 0);
+                            umma_f16(acc + CORR, d_alo + adv, d_whi + adv, IDESC, MERGED ? 1u : (uint32_t)((kb | k) != 0));
+                            umma_f16(acc + CORR, d_ahi + adv, d_wlo + adv, IDESC, 1u);
+                        }
+                        umma_commit(&op_empty[s]);
+                        if (kb == nkb - 1) umma_commit(&acc_full[ab]);
                     }
-                    umma_commit(&op_empty[s]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[ab]);
-                TRACE(tl, 3);
+                if (lane == 0) TRACE(tl, 3);
             }
         }
     } else if (warp < C::EPI_WARP0) {

@@ -72,6 +72,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One lane of a converged warp.  The single-thread roles (TMA producer, MMA issuer) run their loops on ALL lanes and
+// predicate only the issuing instructions with this: tcgen05.mma / cp.async.bulk.tensor take their descriptors, addresses
+// and coordinates from UNIFORM registers, and inside an `if (lane == 0)` region the compiler cannot prove them uniform — it
+// wraps every such instruction in an ELECT / R2UR.BROADCAST x5 / BRA.U.ANY loop, ~90 cycles per MMA and ~170 per TMA
+// operation (profiles/r2m_node_pair_experiment.txt).  In warp-uniform control flow the operands stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 // SiLU with ex2/rcp approximations (~3e-7 relative, below the GEMM's own error): 5 instructions instead of ~25,
 // the epilogue is issue/latency bound otherwise.
 // 16-byte read-only load that does not allocate in L1: the gathered rows are 4 KB apart (they thrash the L1 sets) and

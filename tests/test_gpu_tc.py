@@ -324,17 +324,19 @@ def test_layernorm_split_feeds_presplit_gemm():
     assert err < 6e-6, err
 
 
-@pytest.mark.parametrize("num_atoms", [[4, 11, 20, 8], [20] * 13 + [1, 1, 3], "bench"])
+@pytest.mark.parametrize("num_atoms", [[4, 11, 20, 8], [20] * 13 + [1, 1, 3], "bench128", "bench190", "bench"])
 def test_node_chain_matches_separate_kernels(gold_full, num_atoms):
     """mi_node_chain (one cluster launch per layer boundary: node_mlp.0 -> node_mlp.2 + residual -> next LayerNorm -> next
     P|Q|R GEMM) against the same forward through the separate kernels, and both against the oracle: row counts below,
-    across and far above the 128-row blocks"""
+    across and far above the 128-row blocks.  The library picks the transposed form (rows on the MMA's N side) while the row
+    blocks are at most 64 rows — the first four cases: 8-, 16-, 48- and 64-row blocks — and the row-per-lane form above."""
     import numpy as np
     from oracle import diffcsp_oracle as O
     from test_gpu_parity import _full_module
     from matinvent_b200.models.diffcsp.sample import ATOM_DIST
-    if num_atoms == "bench":
-        num_atoms = np.random.RandomState(0).choice(21, 256, p=ATOM_DIST["mp_20"]).tolist()
+    if isinstance(num_atoms, str):
+        n = {"bench": 256, "bench128": 128, "bench190": 190}[num_atoms]
+        num_atoms = np.random.RandomState(0).choice(21, n, p=ATOM_DIST["mp_20"]).tolist()
     na = torch.tensor(num_atoms)
     B, N = len(na), int(na.sum())
     g = torch.Generator().manual_seed(3)
