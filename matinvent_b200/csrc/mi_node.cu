@@ -570,7 +570,7 @@ constexpr int T_OFF_ROW = T_OFF_PART + TM * T_PARTS * 8;      // per-row floats:
 constexpr int T_SMEM = T_OFF_ROW + 6 * TM * 4;
 constexpr int T_EPI_WARPS = 16, T_THREADS = (EPI_WARP0 + T_EPI_WARPS) * 32;      // epilogue work is per (feature, row group): 4 groups in flight
 static_assert(T_SMEM <= 232448, "does not fit the SM");
-static_assert((3 * T_MAX_S + 5) * 8 + 8 <= 512, "barrier block too small");
+static_assert((3 * T_MAX_S + 6) * 8 + 8 <= 512, "barrier block too small");
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -591,6 +591,16 @@ __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
     lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
 }
 
+// the cluster barrier in two halves (every thread: arrive, wait, arrive, wait, ...)
+__device__ __forceinline__ void cl_arrive() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cl_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(T_THREADS, 1)
 node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                     const __grid_constant__ CUtensorMap mapW0, const __grid_constant__ CUtensorMap mapW1,
@@ -604,7 +614,8 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     uint64_t* acc_full = bars + 3 * T_MAX_S;  // [2]
     uint64_t* acc_empty = acc_full + 2;       // [2]
     uint64_t* stat_bar = acc_full + 4;        // partial LayerNorm statistics of all four CTAs have landed (st.async)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 5);
+    uint64_t* own_ready = acc_full + 5;       // this CTA's epilogue warps have written their slice of the next phase's operand
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 6);
     float2* part = reinterpret_cast<float2*>(smem + T_OFF_PART);    // [TM][T_PARTS] partial (mean, M2) of the LayerNorm rows
     float* s_rowsc0 = reinterpret_cast<float*>(smem + T_OFF_ROW);   // 2^e of the row's agg operand
     float* s_osc0 = s_rowsc0 + TM;                                  // 2^-e of the row's an1 operand
@@ -632,6 +643,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             mbar_init(&acc_empty[b], T_EPI_WARPS);
         }
         mbar_init(stat_bar, 1);
+        mbar_init(own_ready, T_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -652,8 +664,13 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
     const bool tr = threadIdx.x == EPI_WARP0 * 32;                 // the thread that stamps the epilogue side
     (void)tr;
 
-    // Cluster barriers, the same sequence in every thread:  B0 after the prologue, B1 after phase 0 and, with a LayerNorm
-    // phase, B2 (LN(h) operand written) before phase 2.
+    // Operand hand-offs between the phases: B0 after the prologue (agg -> xs), B1 after phase 0 (an1 -> ys) and, with a LayerNorm
+    // phase, B2 (LN(h) -> xs) before phase 2.  Every CTA writes its 128-column slice of the operand — i.e. 4 of the next
+    // phase's 16 k-blocks — and the cluster barrier (release of those global stores to the peers' TMA reads) costs 3-4k cycles.
+    // The barrier is therefore split: a CTA starts the next phase on its OWN slice as soon as its own epilogue warps have
+    // written it (own_ready: CTA-local), and only the other 12 k-blocks wait for the cluster.  The k-blocks of a phase are
+    // walked from the CTA's own slice on: kb = (4 rank + i) mod 16.  Every thread arrives and waits in strict alternation; the
+    // MMA and epilogue warps need nothing the barrier orders, so they wait late (when it has long completed).
     if (warp == 0) {
         // ===================== TMA producer =====================
         uint32_t ws = 0, wph = 0, as = 0;                          // ring positions of the W and the A loads (slot, wrap parity)
@@ -664,7 +681,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             const CUtensorMap* mA = phx == 1 ? &mapY : &mapX;
             const CUtensorMap* mW = phx == 0 ? &mapW0 : (phx == 1 ? &mapW1 : &mapW2);
             auto issue_w = [&](uint32_t loc) {
-                const int tl = (int)(loc / (uint32_t)NKB), kb = (int)(loc % (uint32_t)NKB);
+                const int tl = (int)(loc / (uint32_t)NKB), kb = (int)((loc + 4u * (uint32_t)crank) % (uint32_t)NKB);
                 const int n0 = (crank * ntl + tl) * TN;
                 mbar_wait(&op_empty[ws], wph ^ 1);
                 if (elect_one()) {
@@ -676,11 +693,13 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             };
             // the weights do not depend on the previous phase: the first ring-full of W tiles crosses the barrier
             // (all lanes run the loops, one elected lane issues: see elect_one())
+            cl_arrive();                                           // B0 / B1 / B2: nothing of this warp to release
             for (uint32_t loc = 0; loc < pre; ++loc) issue_w(loc);
-            cluster_sync_all();                                    // B0 / B1 / B2
+            mbar_wait(own_ready, (uint32_t)phx & 1u);              // own slice written (generic -> async proxy fenced by the writers)
             for (uint32_t loc = 0; loc < total; ++loc) {
+                if (loc == 4) cl_wait();                           // the peers' slices
                 if (loc >= pre) issue_w(loc);
-                const int kb = (int)(loc % (uint32_t)NKB);
+                const int kb = (int)((loc + 4u * (uint32_t)crank) % (uint32_t)NKB);
                 if (elect_one()) {
                     mbar_expect_tx(&a_full[as], (uint32_t)(2 * R * TK * 2));
                     tma_load_3d(ring + as * p.slot_bytes, mA, &a_full[as], kb * TK, m0, 0);     // A_hi (R x 64 B) | A_lo right behind it
@@ -705,7 +724,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         uint32_t gt = 0, s = 0, par = 0;                           // tiles so far; ring position (slot, wrap parity)
         for (int phx = 0; phx < p.n_phases; ++phx) {
             const int ntl = phx == 2 ? 3 : 1;
-            cluster_sync_all();                                    // B0 / B1 / B2
+            cl_arrive();                                           // B0 / B1 / B2 (waited for after the phase's MMAs)
             {
                 for (int tl = 0; tl < ntl; ++tl, ++gt) {
                     const uint32_t ab = gt & 1;
@@ -738,6 +757,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                 }
             }
             __syncwarp();
+            cl_wait();
         }
     } else {
         // ===================== prologue + epilogue warps (w2..17) =====================
@@ -795,8 +815,16 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                     *reinterpret_cast<float4*>(p.agg + (long long)(m0 + rl) * p.ld_agg + crank * TN + (t & 31) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        // hand-off of this CTA's slice of an operand: own producer first (CTA-local), then the cluster
+        auto handoff = [&]() {
+            asm volatile("fence.proxy.async;" ::: "memory");   // this thread's global stores -> visible to TMA reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(own_ready);
+            cl_arrive();
+        };
         if (tr) NTRACE(2);
-        cluster_sync_all();                                    // B0 (also orders the per-row scalars above for the whole CTA)
+        handoff();                                             // B0
+        asm volatile("bar.sync 1, %0;" ::"n"(T_EPI_WARPS * 32) : "memory");     // the per-row scalars above
         if (tr) NTRACE(3);
 
         uint32_t v[8], w[8];
@@ -840,7 +868,8 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             if (lane == 0) mbar_arrive(&acc_empty[0]);
         }
         if (tr) NTRACE(5);
-        cluster_sync_all();                                    // B1
+        cl_wait();                                             // (B0, long complete)
+        handoff();                                             // B1
         if (tr) NTRACE(6);
 
         // ---- phase 1 epilogue: h = h_in + silu(acc + b_n2); the finished values stay in TMEM (over their accumulator) for
@@ -940,9 +969,10 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[1]);
+            cl_wait();                                         // (B1)
             if (p.n_phases == 3) {
                 if (tr) NTRACE(10);
-                cluster_sync_all();                            // B2
+                handoff();                                     // B2
                 if (tr) NTRACE(11);
             }
         }
@@ -992,6 +1022,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                 if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
             if (tr) NTRACE(15);
+            cl_wait();                                         // (B2)
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
