@@ -696,8 +696,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             cl_arrive();                                           // B0 / B1 / B2: nothing of this warp to release
             for (uint32_t loc = 0; loc < pre; ++loc) issue_w(loc);
             mbar_wait(own_ready, (uint32_t)phx & 1u);              // own slice written (generic -> async proxy fenced by the writers)
-            for (uint32_t loc = 0; loc < total; ++loc) {
-                if (loc == 4) cl_wait();                           // the peers' slices
+            auto issue_a = [&](uint32_t loc) {
                 if (loc >= pre) issue_w(loc);
                 const int kb = (int)((loc + 4u * (uint32_t)crank) % (uint32_t)NKB);
                 if (elect_one()) {
@@ -706,7 +705,10 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                 }
                 __syncwarp();
                 if (++as == S) as = 0;
-            }
+            };
+            for (uint32_t loc = 0; loc < 4; ++loc) issue_a(loc);   // own slice
+            cl_wait();                                             // the peers' slices
+            for (uint32_t loc = 4; loc < total; ++loc) issue_a(loc);
             if (phx + 1 < p.n_phases && elect_one()) {
                 const CUtensorMap* nA = phx == 0 ? &mapY : &mapX;
                 const CUtensorMap* nW = phx == 0 ? &mapW1 : &mapW2;
