@@ -312,8 +312,15 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                     if (n0 == 0 && cg == 0) p.bound_out[mrow] = bound;
                 }
                 const float osc = pow2f(-exp8(bound));
-                const float* prow = p.P + (long long)i1 * p.ld_pq;
-                const float* qrow = p.Q + (long long)i2 * p.ld_pq;
+                const float* prow = p.P + (long long)i1 * p.ld_pq + n0 + cg * WCOLS;
+                const float* qrow = p.Q + (long long)i2 * p.ld_pq + n0 + cg * WCOLS;
+                // the first group's gathered rows are fetched before the accumulators are complete (their L2 latency hides behind
+                // the end of the main loop); the other groups' behind the TMEM read (one group ahead for all of them spilled)
+                float gp[16], gq[16];
+                ldnc8(prow, gp);
+                ldnc8(prow + 8, gp + 8);
+                ldnc8(qrow, gq);
+                ldnc8(qrow + 8, gq + 8);
                 mbar_wait(&acc_full[ab], ((uint32_t)tl >> 1) & 1);
                 if (threadIdx.x == 64) ETRACE(tl, 6);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -322,11 +329,12 @@ edge_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constan
                     const int n = n0 + cg * WCOLS + gi * 16;
                     uint32_t v16[16];
                     tmem_ld16(tbase + (uint32_t)(gi * 16), v16);
-                    float gp[16], gq[16];                // the two gathered rows: in flight behind the TMEM read
-                    ldnc8(prow + n, gp);
-                    ldnc8(prow + n + 8, gp + 8);
-                    ldnc8(qrow + n, gq);
-                    ldnc8(qrow + n + 8, gq + 8);
+                    if (gi > 0) {
+                        ldnc8(prow + gi * 16, gp);
+                        ldnc8(prow + gi * 16 + 8, gp + 8);
+                        ldnc8(qrow + gi * 16, gq);
+                        ldnc8(qrow + gi * 16 + 8, gq + 8);
+                    }
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (gi == WCOLS / 16 - 1) {         // all of this warp's TMEM reads are done: release the accumulators
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

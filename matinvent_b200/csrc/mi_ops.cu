@@ -298,9 +298,11 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N
 // CTA per crystal.  As separate launches these were 3 (corrector) / 7 (predictor) latency-bound kernels of ~15 us each for
 // 0.3 GFLOP; here the crystal's rows are normalised into shared memory once (same arithmetic as layernorm_fwd_kernel) and
 // every warp takes output columns: the weight row sits in registers, the rows come from shared memory.
+// NT threads: 256 with two CTAs per SM; 512 (one per SM) when there are no more crystals than SMs — the kernel is a chain of
+// L2 round trips per warp (LayerNorm rows, then the weight rows of four output columns at a time), twice the warps halve it.
 constexpr int HEAD_ROWS = 32;                       // rows per pass through shared memory
-template <int NV>                                   // H = 32 * NV
-__global__ void __launch_bounds__(256, 2) output_heads_kernel(const float* __restrict__ h, int ldh, const int* __restrict__ node_off,
+template <int NV, int NT>                           // H = 32 * NV
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) output_heads_kernel(const float* __restrict__ h, int ldh, const int* __restrict__ node_off,
                                                               const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                               float eps, const float* __restrict__ coord_w, float* __restrict__ pred_x,
                                                               const float* __restrict__ type_w, const float* __restrict__ type_b, int A,
@@ -1096,13 +1098,20 @@ static int launch_heads(const float* h, int ldh, const int* node_off, int B, con
                         const float* lattice_w, const float* L, int ip, float* pred_l, cudaStream_t s) {
     constexpr int H = 32 * NV;
     const size_t smem = ((size_t)HEAD_ROWS * H + H + 16) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        MI_CUDA(cudaFuncSetAttribute(output_heads_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+    static int sms = 0;
+    if (sms == 0) {
+        MI_CUDA(cudaFuncSetAttribute(output_heads_kernel<NV, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MI_CUDA(cudaFuncSetAttribute(output_heads_kernel<NV, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        MI_CUDA(cudaGetDevice(&dev));
+        MI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    output_heads_kernel<NV><<<B, 256, smem, s>>>(h, ldh, node_off, ln_g, ln_b, eps, coord_w, pred_x, type_w, type_b, A, pred_a,
-                                                 lattice_w, L, ip, pred_l);
+    if (B <= sms)
+        output_heads_kernel<NV, 512><<<B, 512, smem, s>>>(h, ldh, node_off, ln_g, ln_b, eps, coord_w, pred_x, type_w, type_b, A, pred_a,
+                                                          lattice_w, L, ip, pred_l);
+    else
+        output_heads_kernel<NV, 256><<<B, 256, smem, s>>>(h, ldh, node_off, ln_g, ln_b, eps, coord_w, pred_x, type_w, type_b, A, pred_a,
+                                                          lattice_w, L, ip, pred_l);
     MI_CHECK_LAUNCH();
     return MI_OK;
 }
