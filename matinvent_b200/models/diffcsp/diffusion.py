@@ -311,12 +311,27 @@ class _StepState:
             self._body(with_noise=not last)          # first step doubles as warm-up for the capture
         else:
             if self.graph is None:
-                torch.cuda.synchronize()
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._body(with_noise=True)
+                self.graph = capture_graph(lambda: self._body(with_noise=True))
             self.graph.replay()
         self.steps_done += 1
+
+
+def capture_graph(body):
+    """One CUDA graph of `body()`, captured on a side stream with capture_begin / capture_end by hand: the
+    `torch.cuda.graph` context also runs gc.collect(), torch.cuda.empty_cache() and a device synchronize — 0.1-0.15 s per
+    sampled batch / fine-tune epoch (scripts/probe_e2e.py), 4-5 % of a 256-crystal sampling pass."""
+    graph = torch.cuda.CUDAGraph()
+    cur = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        graph.capture_begin()
+        try:
+            body()
+        finally:
+            graph.capture_end()
+    cur.wait_stream(side)
+    return graph
 
 
 class _SampleLoss(torch.autograd.Function):

@@ -23,7 +23,7 @@ import torch
 
 from ... import ops
 from .cspnet import MAX_ATOMIC_NUM
-from .diffusion import PhiloxNoise, TorchNoise
+from .diffusion import PhiloxNoise, TorchNoise, capture_graph
 from .sample import CrystalBatch
 
 
@@ -210,10 +210,7 @@ class FineTuner:
                 grp["body"]()
             else:
                 if grp["graph"] is None:
-                    torch.cuda.synchronize()
-                    grp["graph"] = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(grp["graph"]):
-                        grp["body"]()
+                    grp["graph"] = capture_graph(grp["body"])
                 grp["graph"].replay()
             grp["runs"] += 1
             t += Gn
