@@ -130,7 +130,10 @@ int mi_tc_gemm_presplit(int M, int N, int K, const void* A_hi, const void* A_lo,
  *            receives the row maxima of pqr
  * n_phases = 2 stops after phase 1's residual (last layer).  bounds: 3 device floats {max_j ||W_b[j]||_1, max |bn1|,
  * sqrt(H) max |ln_g| + max |ln_b|} (each rounded UP): the row scales of ys and of the LN operand come from these a-priori
- * bounds of the row maxima, not from the maxima.  Replaces four launches (mi_tc_gemm x3 + mi_layernorm_fwd_split). */
+ * bounds of the row maxima, not from the maxima.  Replaces four launches (mi_tc_gemm x3 + mi_layernorm_fwd_split).
+ * The library runs one of two kernels with identical results up to the FP32-grade rounding of the products: rows on the MMA's
+ * N side while the row blocks it forms are at most 64 rows, rows on the M side above (MI_NODE_T=0 / 1 forces one form,
+ * MI_NODE_ROWS the rows per block: developer switches, read once per process). */
 int mi_node_chain(int M, int H, int n_phases, float* agg, int ld_agg, const float* amax_agg, int zero_agg, void* xs_hi,
                   void* xs_lo, void* ys_hi, void* ys_lo, const void* wb_hi, const void* wb_lo, int ld_wb, const float* bn1,
                   const float* R, int ld_r, const float* amax_pqr, const float* bounds, const void* w2_hi, const void* w2_lo,

@@ -28,6 +28,13 @@
 //
 // Arithmetic of the products: mi_tc.cu's two-accumulator format (split-precision FP16 x3 on tcgen05, TMEM accumulators).
 // Warps: w0 TMA producer, w1 MMA issuer, w2-9 prologue + epilogue.  H = 512 only; other sizes use the separate kernels.
+//
+// Two forms of the same chain, chosen by the host from the row-block size (mi_node_chain, below):
+//   node_chain_kernel     rows on the MMA's M side, a thread of the epilogue owns one ROW (this first half of the file);
+//   node_chain_t_kernel   the operands swapped, rows on the N side, a thread owns one FEATURE (second half): faster while the
+//                         row blocks are short (<= 64 rows: the strong-scaling regime, 128 crystals per GPU), with the operand
+//                         hand-offs between the phases starting on the CTA's own slice.
+// The producer / issuer loops of both run on all 32 lanes with the issuing instructions under elect.sync (mi_tc_common.cuh).
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
