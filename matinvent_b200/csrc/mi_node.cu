@@ -575,7 +575,10 @@ constexpr int T_RING = 200 * 1024, T_MAX_S = 12, T_PARTS = 16;
 constexpr int T_OFF_BAR = T_RING, T_OFF_PART = T_OFF_BAR + 512;
 constexpr int T_OFF_ROW = T_OFF_PART + TM * T_PARTS * 8;      // per-row floats: rowsc0 | osc0 | rowsc1 | mean | rstd | (int) crystal
 constexpr int T_SMEM = T_OFF_ROW + 6 * TM * 4;
-constexpr int T_EPI_WARPS = 16, T_THREADS = (EPI_WARP0 + T_EPI_WARPS) * 32;      // epilogue work is per (feature, row group): 4 groups in flight
+#ifndef MI_NODE_T_WARPS
+#define MI_NODE_T_WARPS 16
+#endif
+constexpr int T_EPI_WARPS = MI_NODE_T_WARPS, T_THREADS = (EPI_WARP0 + T_EPI_WARPS) * 32, T_CG = T_EPI_WARPS / 4;   // epilogue work is per (feature, row group): T_CG groups in flight
 static_assert(T_SMEM <= 232448, "does not fit the SM");
 static_assert((3 * T_MAX_S + 6) * 8 + 8 <= 512, "barrier block too small");
 
@@ -796,12 +799,12 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
         }
         // ---- prologue: this CTA's 128-column slice of agg -> fp16 (hi, lo) pairs, rows scaled from their maxima
 #pragma unroll 1
-        for (int pg = 0; pg < 2; ++pg) {
+        for (int pg = 0; pg < TM / (4 * T_EPI_WARPS); ++pg) {
             float4 vv[4];
             float am[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int rl = (pg * 4 + u) * 16 + (t >> 5);
+                const int rl = (pg * 4 + u) * T_EPI_WARPS + (t >> 5);
                 vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 am[u] = 0.f;
                 if (rl < nvalid) {
@@ -811,7 +814,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int rl = (pg * 4 + u) * 16 + (t >> 5);
+                const int rl = (pg * 4 + u) * T_EPI_WARPS + (t >> 5);
                 if (rl >= nvalid) continue;
                 const float sc = pow2f(-exp8(am[u]));
                 uint2 hh, ll;
@@ -851,13 +854,13 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             if (tr) NTRACE(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int j = cg; j < ngroups; j += 4) {
+            for (int j = cg; j < ngroups; j += T_CG) {
                 const int r0 = j * 8;
                 tmem_ld8(tlane + (uint32_t)r0, v);
                 tmem_ld8(tlane + (uint32_t)(R + r0), w);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = gn[u];
-                if (j + 4 < ngroups) fetch(j + 4);
+                if (j + T_CG < ngroups) fetch(j + T_CG);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -897,13 +900,13 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
             if (tr) NTRACE(7);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int j = cg; j < ngroups; j += 4) {
+            for (int j = cg; j < ngroups; j += T_CG) {
                 const int r0 = j * 8;
                 tmem_ld8(tb + (uint32_t)r0, v);
                 tmem_ld8(tb + (uint32_t)(R + r0), w);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = gn[u];
-                if (j + 4 < ngroups) fetch(j + 4);
+                if (j + T_CG < ngroups) fetch(j + T_CG);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -958,7 +961,7 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                 asm volatile("bar.sync 1, %0;" ::"n"(T_EPI_WARPS * 32) : "memory");
                 const float osc = pow2f(-exp8(ln_bound));
 #pragma unroll 1
-                for (int j = cg; j < ngroups; j += 4) {
+                for (int j = cg; j < ngroups; j += T_CG) {
                     const int r0 = j * 8;
                     tmem_ld8(tb + (uint32_t)r0, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -1006,13 +1009,13 @@ node_chain_t_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_const
                 if (tr) NTRACE(12 + tl);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int j = cg; j < ngroups; j += 4) {
+                for (int j = cg; j < ngroups; j += T_CG) {
                     const int r0 = j * 8;
                     tmem_ld8(tb + (uint32_t)r0, v);
                     tmem_ld8(tb + (uint32_t)(R + r0), w);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) x[u] = gn[u];
-                    if (j + 4 < ngroups) fetch(j + 4);
+                    if (j + T_CG < ngroups) fetch(j + T_CG);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     uint32_t mx = 0;
 #pragma unroll
