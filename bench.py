@@ -123,8 +123,8 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of edge_pair_kernel<0> at the default workload, from the committed
-# ncu --set full capture (profiles/r2_edge_pair_ncu_raw.csv)
-PAIR_TRAFFIC = 146.9e6      # 118.8 MB read + 28.1 MB written
+# ncu --set full capture of the final build (profiles/r2x_b256_ncu_raw.csv; r2_edge_pair_ncu_raw.csv had 118.8 + 28.1 MB)
+PAIR_TRAFFIC = 149.4e6      # 118.9 MB read + 30.5 MB written
 
 WORKLOAD = "DiffCSP CSPNet(H512,L6,F128,fc) 1000-step sampler, batch=%d mp_20 crystals/GPU"
 
@@ -362,7 +362,7 @@ def main():
     kname = ("edge_pair_kernel<0> (tcgen05.mma.cta_group::2, split-precision FP16 x3, both operands staged by TMA)" if pair else
              "tc_gemm_kernel (tcgen05, split-precision FP16 x3)" if dec.use_tc else "sgemm_kernel (FP32 FFMA)")
     # DRAM traffic of this launch from the committed ncu --set full capture of the default workload
-    # (profiles/r1b_tc_gemm_ncu_raw.csv, tc_gemm_kernel<256,1,1,1>: dram__bytes_read.sum 123.3 MB + dram__bytes_write.sum 35.6 MB)
+    # (profiles/r2x_b256_ncu_raw.csv, edge_pair_kernel<0>)
     traffic = PAIR_TRAFFIC if (pair and g.E == 34445) else None
     roofline = dict(bound="tensor", kernel=kname + ": per-edge GEMM 1 (Phi.W_F^T + 2 gathered rows + SiLU), the largest launch",
                     achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf, traffic=traffic,
