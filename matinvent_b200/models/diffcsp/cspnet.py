@@ -548,12 +548,30 @@ class CSPNet(nn.Module):
             ops.segment_reduce(ws.a2, g.seg_ptr, agg, N, H, mean=True, amax_out=ws.amax_agg[i])
 
     # ------------------------------------------------------------------ forward
-    def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None, reuse_embedding=False):
+    def _composed(self, a, train):
+        """inference: the two embedding linears run as one tensor-core GEMM over the composed weight (see _refresh_tc)"""
+        return (not train and self.use_tc and self.compose_embedding and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0)
+
+    def time_term_table(self, ttab, a):
+        """[rows of ttab, H]: the per-crystal embedding term `temb W_t^T + bias` (cspnet.py:267-271) of EVERY timestep.  While
+        sampling all crystals share the time, so the per-step [B, time_dim] x [time_dim, H] GEMM (12 us of latency per reverse
+        step) becomes one GEMM per sampling run and a row gather per step (mi_sampler_step_begin on this table).  Same kernel,
+        same row arithmetic as the per-step call; `a` is the atom-type state the forward will see (it decides the bias)."""
+        if self.use_tc:
+            self._refresh_tc()
+        bias = self._emb_bias if self._composed(a, False) else self._views["lat_b"]
+        out = torch.empty(ttab.shape[0], self.hidden_dim, device=ttab.device, dtype=torch.float32)
+        self._linear(ttab.contiguous(), "lat_w_t", out, ttab.shape[0], bias=bias)
+        return out
+
+    def forward_graph(self, g, temb, a, x, l, train=False, heads=(True, True, True), ws=None, reuse_embedding=False,
+                      tb_ready=False):
         """Score network on a prebuilt graph.  temb [B,T], a [N,A], x [N,3], l [B,3,3] fp32 CUDA.
         heads = which of (lattice, coord, type) outputs to compute.  Returns views into the workspace.
         reuse_embedding: temb, a and l are those of the previous call on this workspace (only x moved, as between the
         corrector and the predictor of one reverse step): the embedding GEMMs and the per-crystal lattice terms of
-        that call are kept."""
+        that call are kept.
+        tb_ready: the caller has already put the per-crystal time term into ws.tb (rows of time_term_table); temb is unused."""
         W, H, F = self._views, self.hidden_dim, self.num_freqs
         N, E, B, L = g.N, g.E, g.B, self.num_layers
         ws = ws or self.workspace(g, train)
@@ -571,19 +589,21 @@ class CSPNet(nn.Module):
         ops.edge_fourier(x, g.edge_src, g.edge_dst, g.cell_off, E, F, None, ws.phi if (train or not presplit) else None,
                          ws.phi_hi if presplit else None, ws.phi_lo if presplit else None,
                          op_scale=2.0 ** 14 if merged else 1.0, lo_scale=1.0 if merged else 2048.0)
-        composed = (not train and self.use_tc and self.compose_embedding and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0)
+        composed = self._composed(a, train)
         if not reuse and composed:
             # inference: the two embedding linears as one tensor-core GEMM over the composed weight (see _refresh_tc); the
             # atom-type state has no producer that reports row maxima: one tiny kernel takes them
             ops.row_amax(a, N, self.max_atoms, ws.amax_h0)
-            self._linear(temb, "lat_w_t", ws.tb, B, bias=self._emb_bias)
+            if not tb_ready:
+                self._linear(temb, "lat_w_t", ws.tb, B, bias=self._emb_bias)
             ops.tc_gemm(a, self._emb_hl[0], self._emb_hl[1], ws.h[0], M=N, N=H, K=self.max_atoms,
                         gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
             ops.lattice_ip(l, ws.ips, B)
         elif not reuse:
             # the atom-type state is unbounded (no producer reports its row maxima) and K = 100: FP32 CUDA-core GEMM
             ops.sgemm(a, W["emb_w"], ws.h0, M=N, bias=W["emb_b"], amax_out=ws.amax_h0)
-            self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
+            if not tb_ready:
+                self._linear(temb, "lat_w_t", ws.tb, B, bias=W["lat_b"])
             self._linear(ws.h0, "lat_w_h", ws.h[0], N, gathers=[(ws.tb, g.node_graph)], a_amax=ws.amax_h0)
             ops.lattice_ip(l, ws.ips, B)
         # per-crystal term C_b of the first edge linear, all layers in one launch (the layer blocks of the flat weight

@@ -270,6 +270,8 @@ class _StepState:
         self.ws = module.decoder.workspace(g, False)
         self.coef = co.table().to(dev)
         self.ttab = module.time_table()
+        # all crystals of a reverse step share the time: the per-crystal time term of the embedding for every timestep, once
+        self.tbtab = module.decoder.time_term_table(self.ttab, a)
         self.t_dev = torch.full((1,), T0, dtype=torch.int32, device=dev)
         self.in_graph_noise = isinstance(noise, PhiloxNoise)
         self.use_graph = use_graph
@@ -291,15 +293,15 @@ class _StepState:
         m, g, ws = self.m, self.g, self.ws
         B, N, A = g.B, g.N, MAX_ATOMIC_NUM
         dec = m.decoder
-        ops.sampler_step_begin(self.t_dev, self.ttab, self.temb, B, m.time_dim)
+        ops.sampler_step_begin(self.t_dev, self.tbtab, ws.tb, B, dec.hidden_dim)     # ws.tb = row t of the time-term table
         if with_noise and self.in_graph_noise:
             self.noise.fill(self.znoise)
         nz = (lambda t: t) if with_noise else (lambda t: None)
         # corrector: only the coordinate head is consumed (diffusion.py:327-330)
-        _, px, _ = dec.forward_graph(g, self.temb, self.a, self.x, self.l, heads=(False, True, False), ws=ws)
+        _, px, _ = dec.forward_graph(g, self.temb, self.a, self.x, self.l, heads=(False, True, False), ws=ws, tb_ready=True)
         ops.reverse_corrector(self.x, px, nz(self.zx_c), self.x_half, N, self.coef, self.t_dev)
         # predictor (diffusion.py:345-351)
-        pl, px, pa = dec.forward_graph(g, self.temb, self.a, self.x_half, self.l, ws=ws, reuse_embedding=True)
+        pl, px, pa = dec.forward_graph(g, self.temb, self.a, self.x_half, self.l, ws=ws, reuse_embedding=True, tb_ready=True)
         ops.reverse_predictor(self.x_half, px, nz(self.zx_p), self.x, N, self.l, pl, nz(self.zl), B, self.a, pa,
                               nz(self.za), A, self.coef, self.t_dev)
         ops.sampler_step_end(self.t_dev)
