@@ -556,3 +556,30 @@ def test_forward_benchmark_kernels_small_batches_vs_oracle(style):
     errs = [rel_err(u, r) for u, r in zip(out, ref)]
     print("benchmark kernels, %s graph, %d atoms: %s" % (style, N, " ".join("%.2e" % e for e in errs)))
     assert max(errs) < 2e-5, errs
+
+
+def test_time_term_table_matches_per_step_linear(gold_full):
+    """CSPNet.time_term_table (the per-crystal time term `temb W_t^T + b` of every timestep, one GEMM per sampling run) holds
+    exactly the rows the per-step GEMM of forward_graph writes into ws.tb, and equals the float64 product to FP32-grade
+    accuracy; mi_sampler_step_begin copies row t for every crystal (cspnet.py:267-271, diffusion.py:53-66)."""
+    from matinvent_b200 import ops
+    m = _full_module(gold_full)
+    dec = m.decoder
+    H = dec.hidden_dim
+    ttab = m.time_table()                                     # [T + 1, time_dim]
+    a = torch.randn(37, 100, device="cuda")
+    table = dec.time_term_table(ttab, a)
+    assert table.shape == (ttab.shape[0], H)
+    bias = dec._emb_bias if dec._composed(a, False) else dec.w("lat_b")
+    want = ttab.double() @ dec.w("lat_w_t").double().t() + bias.double()
+    assert rel_err(table, want.float()) < 3e-6
+    # the per-step path: B crystals at one timestep through the same linear
+    B = 5
+    for t in (0, 1, 499, 1000):
+        temb = ttab[t].expand(B, -1).contiguous()
+        tb = torch.empty(B, H, device="cuda")
+        dec._linear(temb, "lat_w_t", tb, B, bias=bias)
+        assert torch.equal(tb, table[t].expand(B, -1)), t
+        out = torch.full((B, H), 7.0, device="cuda")
+        ops.sampler_step_begin(torch.tensor([t], dtype=torch.int32, device="cuda"), table, out, B, H)
+        assert torch.equal(out, table[t].expand(B, -1))
